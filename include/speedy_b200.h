@@ -1,0 +1,89 @@
+/* speedy-b200: C ABI of the B200-native SPEEDY hot path (libspeedy_b200.so).
+ *
+ * Every entry point replaces one procedure of the reference's f2py-facing Fortran module `speedy_driver`
+ * (generated from registry/templates/speedy_driver.f90.j2, result speedy.f90/speedy_driver.f90); the template
+ * line of the procedure each one stands in for is cited.  Handles are opaque 64-bit integers exactly like the
+ * reference's `integer(8)` containers (.j2:8-14,38-39).  Plain pointers and sizes only; no torch types.
+ * Arrays cross the boundary in Fortran order with the registry dtype (complex128 / float64 / float32 / int32),
+ * copies in both directions (docs/user_guide.rst:86-93).  Error codes: 0 ok, -1 state not initialised,
+ * -2 diagnostics out of range (error_codes.f90:7-9).  INTEGRATION.md shows the Fortran iso_c_binding and the
+ * Python ctypes bindings.
+ */
+#ifndef SPEEDY_B200_H
+#define SPEEDY_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "spdy_registry.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- model state (.j2:216-258) ---------------------------------------------------------------------- */
+int64_t spdy_modelstate_init(void);                              /* modelstate_init          .j2:216-223 */
+void spdy_modelstate_init_sst_anom(int64_t state, int n_months); /* modelstate_init_sst_anom .j2:225-238 */
+void spdy_modelstate_close(int64_t state);                       /* modelstate_close         .j2:240-258 */
+
+/* ---- datetime and control containers (.j2:131-210) ---------------------------------------------------- */
+int64_t spdy_create_datetime(int year, int month, int day, int hour, int minute); /* create_datetime .j2:163-186 */
+void spdy_get_datetime(int64_t dt, int *ymdhm /* [5] */);                         /* get_datetime    .j2:188-202 */
+void spdy_close_datetime(int64_t dt);                                             /* close_datetime  .j2:204-210 */
+int64_t spdy_controlparams_init(int64_t start_dt, int64_t end_dt);                /* controlparams_init  .j2:131-148 */
+void spdy_controlparams_close(int64_t control);                                   /* controlparams_close .j2:150-157 */
+
+/* ---- model (.j2:29-125) --------------------------------------------------------------------------------- */
+int spdy_init(int64_t state, int64_t control);                   /* init  .j2:29-41  -> initialization.f90:13-91 */
+int spdy_step(int64_t state, int64_t control);                   /* step  .j2:43-55  -> speedy.f90:20-74          */
+void spdy_parallel_step(const int64_t *states, const int64_t *controls, int *error_codes,
+                        int n_members);                          /* parallel_step .j2:58-79                       */
+int spdy_check(int64_t state);                                   /* check .j2:81-91  (time level 1)               */
+void spdy_transform_spectral2grid(int64_t state);                /* .j2:94-103  -> prognostics.f90:125-154        */
+void spdy_transform_grid2spectral(int64_t state);                /* .j2:105-114 -> prognostics.f90:157-176        */
+void spdy_apply_grid_filter(int64_t state);                      /* .j2:116-125 -> prognostics.f90:180-219        */
+
+/* ---- registry accessors: get_<v> / set_<v> / get_<v>_shape / is_array_<v> (.j2:264-334), var = enum spdy_var */
+int spdy_get(int64_t state, int var, void *dst, size_t bytes);
+int spdy_set(int64_t state, int var, const void *src, size_t bytes);
+int spdy_shape(int64_t state, int var, int *dims /* [5] */, int *ndim);
+
+/* ---- ensemble extensions (no reference counterpart; same semantics as repeated parallel_step) ------------- */
+/* Advance all listed members `nsteps` steps without a host round trip per step; error_codes receives the first
+ * non-zero code of each member (0 if none).  Returns the number of failed members. */
+int spdy_run_steps(const int64_t *states, const int64_t *controls, int n_members, int nsteps, int *error_codes);
+int spdy_reserve(int n_members);            /* pre-size the device arenas */
+int spdy_set_device(int ordinal);           /* select the GPU (before the first state is created) */
+int spdy_synchronize(void);
+/* elapsed device time (ms) of the last spdy_run_steps / spdy_parallel_step call, CUDA events on the launch stream */
+float spdy_last_elapsed_ms(void);
+long long spdy_kernel_launches(void);       /* kernels launched by this library so far */
+/* partial sums for ensemble mean / spread of a grid variable over the listed members:
+ * sum[i] = sum_m x_m[i], sumsq[i] = sum_m (x_m[i]-shift[i])^2, both device-resident results copied to host */
+int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const double *shift, double *sum, double *sumsq);
+/* same, leaving results on the device for an NCCL all-reduce: returns device pointers (2 * nelem doubles) */
+int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **sum_sumsq_dev,
+                              size_t *nelem);
+
+/* ---- stage-level entry points (parity tests, microbenchmarks); host buffers, one field after another -------- */
+int spdy_table(const char *name, double *dst, int cap);
+int spdy_batch_spec2grid(const double *spec /* n x (31,32) complex */, double *grid /* n x (96,48) */, int kcos, int n);
+int spdy_batch_grid2spec(const double *grid, double *spec, int n);
+int spdy_batch_legendre_inv(const double *spec, double *four /* n x (62,48) */, int n);
+int spdy_batch_legendre_dir(const double *four, double *spec, int n);
+int spdy_batch_fourier_inv(const double *four, double *grid, int kcos, int n);
+int spdy_batch_fourier_dir(const double *grid, double *four, int n);
+/* resident round trip for the spectral microbench: n synthetic fields stay in HBM, `reps` x (spec2grid, grid2spec);
+ * returns average device ms per rep; per_kernel_ms[4] = legendre_inv, fft_inv, fft_fwd, legendre_dir */
+int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, float *ms_per_rep, float *per_kernel_ms);
+/* column physics of one member on explicit grid inputs (physics.f90:103-231): (96,48,8) fields, tendencies in/out */
+int spdy_debug_physics(int64_t state, const double *ug8, const double *vg8, const double *tg, const double *qg,
+                       const double *phig, const double *pslg, double *utend8, double *vtend8, double *ttend,
+                       double *qtend, int *dbg /* 3 x (96,48): itop, icnv, icltop */);
+/* one raw leapfrog step(j1, j2, dt) of time_stepping.f90:38-147 without calendar/coupler; dt_kind 0: delt/2, 1: delt, 2: 2*delt */
+int spdy_debug_raw_step(int64_t state, int j1, int j2, int dt_kind);
+int spdy_debug_get_corh(int64_t state, double *tcorh, double *qcorh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

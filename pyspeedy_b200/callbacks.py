@@ -1,0 +1,93 @@
+"""Callbacks: host-side mirror of pyspeedy/callbacks.py (same classes, arguments and behaviour)."""
+import copy
+import os
+
+from pyspeedy_b200 import DEFAULT_OUTPUT_VARS
+from pyspeedy_b200.dataset import Dataset
+from pyspeedy_b200.speedy import Speedy, SpeedyEns  # noqa
+
+
+class BaseCallback:
+    """Base callback class (pyspeedy/callbacks.py:31-75)."""
+
+    def __init__(self, *args, **kwargs):
+        self.verbose = kwargs.pop("verbose", False)
+        self.interval = kwargs.pop("interval", 1)
+        self.spinup_date = kwargs.pop("spinup_date", None)
+
+    def skip_flag(self, model_instance):
+        if self.spinup_date is not None:
+            if model_instance.current_date < self.spinup_date:
+                return True
+        return model_instance.get_current_step() % self.interval != 0
+
+    def print_msg(self, msg):
+        if self.verbose:
+            print(msg)
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+    def __call__(self, model_instance):
+        pass
+
+
+class DiagnosticCheck(BaseCallback):
+    """Check that the prognostic variables are inside reasonable ranges (pyspeedy/callbacks.py:78-112)."""
+
+    def __init__(self, interval=36):
+        super().__init__(interval=interval)
+
+    def __call__(self, model_instance):
+        if self.skip_flag(model_instance):
+            return
+        if isinstance(model_instance, Speedy):
+            model_instance = [model_instance]
+        for _member in model_instance:
+            _member.check()
+
+
+class ModelCheckpoint(BaseCallback):
+    """Keep a time series of selected grid variables in memory (pyspeedy/callbacks.py:115-180)."""
+
+    def __init__(self, interval=36, verbose=False, spinup_date=None, variables=None, output_dir="./"):
+        if variables is None:
+            variables = DEFAULT_OUTPUT_VARS
+        self.variables = variables
+        self.output_dir = output_dir
+        self.history_interval = interval
+        super().__init__(verbose=verbose, interval=interval, spinup_date=spinup_date)
+        self.dataframe = None
+
+    def __call__(self, model_instance):
+        if self.skip_flag(model_instance):
+            return
+        model_df = model_instance.to_dataframe(variables=self.variables)
+        if self.dataframe is None:
+            self.dataframe = model_df
+        else:
+            self.dataframe = Dataset.merge((self.dataframe, model_df))
+
+
+class XarrayExporter(BaseCallback):
+    """Write one NetCDF file per output time (pyspeedy/callbacks.py:183-255)."""
+
+    def __init__(self, interval=36, verbose=False, spinup_date=None, variables=None, output_dir="./",
+                 filename_fmt="%Y-%m-%d_%H%M.nc"):
+        if variables is None:
+            variables = DEFAULT_OUTPUT_VARS
+        self.variables = variables
+        self.output_dir = output_dir
+        self.filename_fmt = filename_fmt
+        self.history_interval = interval
+        super().__init__(verbose=verbose, interval=interval, spinup_date=spinup_date)
+
+    def __call__(self, model_instance):
+        if self.skip_flag(model_instance):
+            return
+        model_df = model_instance.to_dataframe(variables=self.variables)
+        file_name = model_instance.current_date.strftime(self.filename_fmt)
+        os.makedirs(self.output_dir, exist_ok=True)
+        output_file_path = os.path.join(self.output_dir, file_name)
+        self.print_msg(f"Saving model output at: {output_file_path}.")
+        model_df.to_netcdf(output_file_path, encoding=dict())

@@ -1,0 +1,211 @@
+// speedy-b200: stage-level entry points (parity tests, microbenchmarks) and ensemble diagnostics.
+// Fields are treated as pseudo-members: field f lives in lane f % 32 of workspace tile f / 32, so the very same
+// kernels of the model step are exercised.
+namespace spdy {
+
+struct Workspace {
+    double *buf = nullptr;
+    int *tiles = nullptr;
+    unsigned *masks = nullptr;
+    int ntiles = 0;
+    InvDesc *d_inv = nullptr;
+    FwdDesc *d_fwd = nullptr;
+    FwdOut *d_out = nullptr;
+    double *d_lin = nullptr;
+    size_t lin_cap = 0;
+};
+static Workspace W;
+constexpr long long WS_SPEC = 0, WS_FOUR = NSP, WS_GRID = NSP + NFOUR, WS_ELEMS = NSP + NFOUR + NG;
+
+static Ctx ws_ctx(int nfields) {
+    engine_init();
+    const int nt = (nfields + TILE - 1) / TILE;
+    if (nt > W.ntiles) {
+        if (W.buf) CK(cudaFree(W.buf)), CK(cudaFree(W.tiles)), CK(cudaFree(W.masks));
+        CK(cudaMalloc(&W.buf, (size_t)nt * WS_ELEMS * TILE * sizeof(double)));
+        CK(cudaMemset(W.buf, 0, (size_t)nt * WS_ELEMS * TILE * sizeof(double)));
+        std::vector<int> t(nt);
+        std::vector<unsigned> m(nt, 0xffffffffu);
+        for (int i = 0; i < nt; i++) t[i] = i;
+        CK(cudaMalloc(&W.tiles, nt * sizeof(int)));
+        CK(cudaMalloc(&W.masks, nt * sizeof(unsigned)));
+        CK(cudaMemcpy(W.tiles, t.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(W.masks, m.data(), nt * sizeof(unsigned), cudaMemcpyHostToDevice));
+        W.ntiles = nt;
+    }
+    if (!W.d_inv) {
+        CK(cudaMalloc(&W.d_inv, sizeof(InvDesc)));
+        CK(cudaMalloc(&W.d_fwd, sizeof(FwdDesc)));
+        CK(cudaMalloc(&W.d_out, sizeof(FwdOut)));
+        const FwdDesc f{REF_SCR | WS_GRID, 0, 0.0, 2, 0};
+        const FwdOut o{REF_SCR | WS_SPEC};
+        CK(cudaMemcpy(W.d_fwd, &f, sizeof(f), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(W.d_out, &o, sizeof(o), cudaMemcpyHostToDevice));
+    }
+    Ctx c = make_ctx(W.tiles, W.masks, nt);
+    c.scr = W.buf, c.scr_elems = WS_ELEMS, c.st = nullptr;
+    return c;
+}
+static void ws_set_kcos(int kcos) {
+    const InvDesc d{REF_SCR | WS_SPEC, WS_GRID, kcos, 0};
+    CK(cudaMemcpy(W.d_inv, &d, sizeof(d), cudaMemcpyHostToDevice));
+}
+__global__ void k_ws_pack(const double *lin, double *buf, long long off, long long len, long long n, int unpack) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n * len) return;
+    const long long f = i / len, e = i - f * len;
+    double *p = buf + ((f / TILE) * WS_ELEMS + off + e) * TILE + (f % TILE);
+    if (unpack) const_cast<double *>(lin)[i] = *p; else *p = lin[i];
+}
+static void ws_move(const double *host_in, double *host_out, long long off, long long len, int n) {
+    const size_t bytes = (size_t)n * len * sizeof(double);
+    if (bytes > W.lin_cap) {
+        if (W.d_lin) CK(cudaFree(W.d_lin));
+        CK(cudaMalloc(&W.d_lin, bytes));
+        W.lin_cap = bytes;
+    }
+    const long long tot = (long long)n * len;
+    if (host_in) {
+        CK(cudaMemcpy(W.d_lin, host_in, bytes, cudaMemcpyHostToDevice));
+        k_ws_pack<<<(int)((tot + 255) / 256), 256, 0, E.stream>>>(W.d_lin, W.buf, off, len, n, 0);
+        CK(cudaStreamSynchronize(E.stream));
+    } else {
+        k_ws_pack<<<(int)((tot + 255) / 256), 256, 0, E.stream>>>(W.d_lin, W.buf, off, len, n, 1);
+        CK(cudaStreamSynchronize(E.stream));
+        CK(cudaMemcpy(host_out, W.d_lin, bytes, cudaMemcpyDeviceToHost));
+    }
+}
+
+}  // namespace spdy
+
+extern "C" {
+
+int spdy_batch_legendre_inv(const double *spec, double *four, int n) {
+    Ctx c = ws_ctx(n);
+    ws_set_kcos(1);
+    ws_move(spec, nullptr, WS_SPEC, NSP, n);
+    launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    COUNT(1);
+    ws_move(nullptr, four, WS_FOUR, NFOUR, n);
+    return 0;
+}
+int spdy_batch_fourier_inv(const double *four, double *grid, int kcos, int n) {
+    Ctx c = ws_ctx(n);
+    ws_set_kcos(kcos);
+    ws_move(four, nullptr, WS_FOUR, NFOUR, n);
+    launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    COUNT(1);
+    ws_move(nullptr, grid, WS_GRID, NG, n);
+    return 0;
+}
+int spdy_batch_fourier_dir(const double *grid, double *four, int n) {
+    Ctx c = ws_ctx(n);
+    ws_move(grid, nullptr, WS_GRID, NG, n);
+    launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
+    COUNT(1);
+    ws_move(nullptr, four, WS_FOUR, NFOUR, n);
+    return 0;
+}
+int spdy_batch_legendre_dir(const double *four, double *spec, int n) {
+    Ctx c = ws_ctx(n);
+    ws_move(four, nullptr, WS_FOUR, NFOUR, n);
+    launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
+    COUNT(1);
+    ws_move(nullptr, spec, WS_SPEC, NSP, n);
+    return 0;
+}
+int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
+    Ctx c = ws_ctx(n);
+    ws_set_kcos(kcos);
+    ws_move(spec, nullptr, WS_SPEC, NSP, n);
+    launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    COUNT(2);
+    ws_move(nullptr, grid, WS_GRID, NG, n);
+    return 0;
+}
+int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
+    Ctx c = ws_ctx(n);
+    ws_move(grid, nullptr, WS_GRID, NG, n);
+    launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
+    launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
+    COUNT(2);
+    ws_move(nullptr, spec, WS_SPEC, NSP, n);
+    return 0;
+}
+
+int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, float *ms_per_rep, float *per_kernel_ms) {
+    Ctx c = ws_ctx(n);
+    ws_set_kcos(1);
+    ws_move(spec, nullptr, WS_SPEC, NSP, n);
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
+    float acc[4] = {0, 0, 0, 0}, tot = 0.f;
+    for (int r = -2; r < reps; r++) {  // two warm-up reps
+        CK(cudaEventRecord(ev[0], E.stream));
+        launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+        CK(cudaEventRecord(ev[1], E.stream));
+        launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+        CK(cudaEventRecord(ev[2], E.stream));
+        launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
+        CK(cudaEventRecord(ev[3], E.stream));
+        launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
+        CK(cudaEventRecord(ev[4], E.stream));
+        COUNT(4);
+        CK(cudaStreamSynchronize(E.stream));
+        if (r >= 0) {
+            float ms;
+            for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])), acc[i] += ms;
+            CK(cudaEventElapsedTime(&ms, ev[0], ev[4]));
+            tot += ms;
+        }
+    }
+    for (int i = 0; i < 5; i++) CK(cudaEventDestroy(ev[i]));
+    if (reps > 0) {
+        *ms_per_rep = tot / reps;
+        for (int i = 0; i < 4; i++) per_kernel_ms[i] = acc[i] / reps;
+    }
+    if (spec_out) ws_move(nullptr, spec_out, WS_SPEC, NSP, n);
+    return 0;
+}
+
+static double *g_sums = nullptr;
+static size_t g_sums_n = 0;
+int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **out, size_t *nelem) {
+    engine_init();
+    if (var < 0 || var >= SPDY_NVARS || E.off[var] < 0) return -1;
+    const long long n = E.nelem[var];
+    if ((size_t)n > g_sums_n) {
+        if (g_sums) CK(cudaFree(g_sums));
+        CK(cudaMalloc(&g_sums, 2 * n * sizeof(double)));
+        g_sums_n = n;
+    }
+    CK(cudaMemsetAsync(g_sums, 0, 2 * n * sizeof(double), E.stream));
+    const int nt = prepare_members(states, n_members);
+    Ctx c = make_ctx(E.d_tiles, E.d_masks, nt);
+    k_ens_sums<<<(int)((n + 7) / 8), 256, 0, E.stream>>>(c, E.off[var], n, shift_dev, g_sums, g_sums + n);
+    COUNT(1);
+    CK(cudaStreamSynchronize(E.stream));
+    *out = g_sums;
+    *nelem = (size_t)n;
+    return 0;
+}
+int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const double *shift, double *sum, double *sumsq) {
+    engine_init();
+    if (var < 0 || var >= SPDY_NVARS || E.off[var] < 0) return -1;
+    const long long n = E.nelem[var];
+    double *d_shift = nullptr;
+    if (shift) {
+        CK(cudaMalloc(&d_shift, n * sizeof(double)));
+        CK(cudaMemcpy(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    void *dev;
+    size_t ne;
+    spdy_ensemble_sums_device(states, n_members, var, d_shift, &dev, &ne);
+    CK(cudaMemcpy(sum, dev, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sumsq, (double *)dev + n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (d_shift) CK(cudaFree(d_shift));
+    return 0;
+}
+
+}  // extern "C"

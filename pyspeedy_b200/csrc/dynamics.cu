@@ -1,0 +1,344 @@
+// speedy-b200: grid-point dynamics, spectral tendencies + semi-implicit + diffusion + leapfrog, diagnostics,
+// per-member control (calendar) kernels.
+//
+// Reference semantics: tendencies.f90:51-352, implicit.f90:234-289, horizontal_diffusion.f90:131-152,
+// time_stepping.f90:38-188, diagnostics.f90:16-74, model_control.f90:113-186, speedy.f90:20-74.
+// One thread = one (grid column | spectral coefficient) of one member; lane = member.
+#include "kernels.h"
+
+namespace spdy {
+
+// physical constants with the reference's REAL(4)-literal values (physical_constants.f90:15-47)
+__device__ constexpr double D_AKAP = (double)(2.0f / 7.0f);
+__device__ constexpr double D_CP = FL(1004.0);
+__device__ constexpr double D_RGAS = D_AKAP * D_CP;
+__device__ constexpr double D_ROB = FL(0.05), D_WIL = FL(0.53);
+
+// ------------------------------------------------------------------------------------ grid-point dynamics
+// tendencies.f90:132-224.  Inputs: ug, vg, tg, vorg, divg, trg (level j2), px, py.  Outputs: utend, vtend,
+// ttend, trtend and the grid field whose transform is psdt.
+__global__ void __launch_bounds__(128) k_grid_dyn(const Ctx c, const ScratchLayout L) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    const int j = q / IX;
+    const size_t e = (size_t)q * TILE, lev = (size_t)NG * TILE;
+    const double *pu = scp(c, t, L.ug, lane) + e, *pv = scp(c, t, L.vg, lane) + e, *pt = scp(c, t, L.tg, lane) + e,
+                 *pvo = scp(c, t, L.vorg, lane) + e, *pd = scp(c, t, L.divg, lane) + e, *pq = scp(c, t, L.trg, lane) + e;
+    double u[KX], v[KX], T[KX], vo[KX], d[KX], tr[KX];
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        u[k] = pu[k * lev], v[k] = pv[k * lev], T[k] = pt[k * lev];
+        vo[k] = pvo[k * lev] + c_T.coriol[j];  // :126-130
+        d[k] = pd[k * lev], tr[k] = pq[k * lev];
+    }
+    const double px = *(scp(c, t, L.px, lane) + e), py = *(scp(c, t, L.py, lane) + e);
+    double umean = 0.0, vmean = 0.0, dmean = 0.0;
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        umean = umean + u[k] * c_T.dhs[k];
+        vmean = vmean + v[k] * c_T.dhs[k];
+        dmean = dmean + d[k] * c_T.dhs[k];
+    }
+    *(scp(c, t, L.psdtg, lane) + e) = -umean * px - vmean * py;  // :148
+    double puv[KX], sigdt[KX + 1], sigm[KX + 1], tgg[KX];
+    sigdt[0] = 0.0, sigm[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        puv[k] = (u[k] - umean) * px + (v[k] - vmean) * py;
+        sigdt[k + 1] = sigdt[k] - c_T.dhs[k] * (puv[k] + d[k] - dmean);
+        sigm[k + 1] = sigm[k] - c_T.dhs[k] * puv[k];
+        tgg[k] = T[k] - c_T.tref[k];
+    }
+    double *ou = scp(c, t, L.utend, lane) + e, *ov = scp(c, t, L.vtend, lane) + e, *ot = scp(c, t, L.ttend, lane) + e,
+           *oq = scp(c, t, L.trtend, lane) + e;
+    double tmp[KX + 1];
+    tmp[0] = 0.0, tmp[KX] = 0.0;
+    // zonal wind :174-184
+#pragma unroll
+    for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (u[k] - u[k - 1]);
+#pragma unroll
+    for (int k = 0; k < KX; k++) ou[k * lev] = v[k] * vo[k] - tgg[k] * D_RGAS * px - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+    // meridional wind :187-194
+#pragma unroll
+    for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (v[k] - v[k - 1]);
+#pragma unroll
+    for (int k = 0; k < KX; k++) ov[k * lev] = -u[k] * vo[k] - tgg[k] * D_RGAS * py - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+    // temperature :197-209
+#pragma unroll
+    for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (tgg[k] - tgg[k - 1]) + sigm[k] * (c_T.tref[k] - c_T.tref[k - 1]);
+#pragma unroll
+    for (int k = 0; k < KX; k++)
+        ot[k * lev] = tgg[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k] + c_T.fsgr[k] * tgg[k] * (sigdt[k + 1] + sigdt[k]) +
+                      c_T.tref3[k] * (sigm[k + 1] + sigm[k]) + D_AKAP * (T[k] * puv[k] - tgg[k] * dmean);
+    // tracer :212-224 (temp(:,:,2:3) = 0)
+#pragma unroll
+    for (int k = 1; k < KX; k++) tmp[k] = (k <= 2) ? 0.0 : sigdt[k] * (tr[k] - tr[k - 1]);
+#pragma unroll
+    for (int k = 0; k < KX; k++) oq[k * lev] = tr[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+}
+
+// -------------------------------------------------------------------------- spectral tendencies + time step
+struct C2 {
+    double r, i;
+};
+__device__ __forceinline__ C2 ld2(const double *p) { return {p[0], p[TILE]}; }
+__device__ __forceinline__ void st2(double *p, C2 v) { p[0] = v.r, p[TILE] = v.i; }
+__device__ __forceinline__ C2 operator+(C2 a, C2 b) { return {a.r + b.r, a.i + b.i}; }
+__device__ __forceinline__ C2 operator-(C2 a, C2 b) { return {a.r - b.r, a.i - b.i}; }
+__device__ __forceinline__ C2 operator*(double s, C2 a) { return {s * a.r, s * a.i}; }
+__device__ __forceinline__ C2 operator*(C2 a, double s) { return {a.r * s, a.i * s}; }
+__device__ __forceinline__ C2 operator-(C2 a) { return {-a.r, -a.i}; }
+
+// (vor, div) of vel2vort at coefficient (m,n) from spectral u, v (spectral.f90:160-186)
+__device__ __forceinline__ void vdspec_elem(const GlobTables *G, const double *su, const double *sv, int m, int n,
+                                            C2 &vor, C2 &dv) {
+    const int q = m + MX * n;
+    const size_t up = (size_t)M2 * TILE;
+    const double gx = G->gradx[m];
+    const C2 uc = ld2(su), vc = ld2(sv);
+    const C2 zp = {-(gx * uc.i), gx * uc.r}, zc = {-(gx * vc.i), gx * vc.r};
+    if (n == 0) {
+        const double yp = G->vddyp[q];
+        vor = zc - yp * ld2(su + up);
+        dv = zp + yp * ld2(sv + up);
+    } else if (n == NX - 1) {
+        const double ym = G->vddym[q];
+        vor = ym * ld2(su - up);
+        dv = (-ym) * ld2(sv - up);
+    } else {
+        const double ym = G->vddym[q], yp = G->vddyp[q];
+        vor = (ym * ld2(su - up) - yp * ld2(su + up)) + zc;
+        dv = ((-ym) * ld2(sv - up) + yp * ld2(sv + up)) + zp;
+    }
+}
+
+// leapfrog + Robert-Asselin-Williams filter on one coefficient (time_stepping.f90:164-188)
+__device__ __forceinline__ void raw_update(double *p1, double *p2, C2 fdt, double trf, int j1, double dt, double eps,
+                                           bool act) {
+    fdt = fdt * trf;  // truncate (ix == 4*iy)
+    C2 o1 = ld2(p1), o2 = ld2(p2);
+    const C2 fnew = o1 + dt * fdt;
+    C2 oj1 = (j1 == 1) ? o1 : o2;
+    o1 = oj1 + (D_WIL * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (j1 == 1) oj1 = o1;  // output(:,:,j1) aliases the updated level 1
+    o2 = fnew - ((1.0 - D_WIL) * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (act) {
+        st2(p1, o1);
+        st2(p2, o2);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_spec_step(const Ctx c, const ScratchLayout L, const int j1, const double dt,
+                                                   const double eps, const int impl_idx) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const GlobTables *G = c.G;
+    const ImplTables *I = &G->impl[impl_idx];
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE, lev = (size_t)NSP * TILE;
+    const bool act = lane_active(c, t, lane);
+    const double *F = scp(c, t, L.sfwd, lane) + e;  // forward-transform outputs, slot s at F + s*lev
+    // state, time level 1 (0-based 0) and 2
+    double *vor = stp(c, t, c.off[V_vor], lane) + e, *dvs = stp(c, t, c.off[V_div], lane) + e,
+           *tt = stp(c, t, c.off[V_t], lane) + e, *trs = stp(c, t, c.off[V_tr], lane) + e,
+           *ps = stp(c, t, c.off[V_ps], lane) + e;
+    const double *phi = stp(c, t, c.off[V_phi], lane) + e;
+    const size_t tl = (size_t)KX * lev;  // time-level stride of (mx,nx,kx,2) arrays
+    const double el2 = G->el2[q], trf = G->trfilt[q];
+
+    C2 divdt[KX], tdt[KX];
+    // ---- A. grid-point tendencies converted to spectral space (tendencies.f90:238-268)
+    // vorticity tendency is final after diffusion: handle it level by level at the end (needs no vertical coupling)
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        C2 vo, dv;
+        vdspec_elem(G, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, m, n, vo, dv);
+        const C2 ke = ld2(F + (FW_KE + k) * lev);
+        divdt[k] = dv - ((-ke) * el2);
+        C2 dum, dT;
+        vdspec_elem(G, F + (FW_UT + k) * lev, F + (FW_VT + k) * lev, m, n, dum, dT);
+        tdt[k] = dT + ld2(F + (FW_TT + k) * lev);
+    }
+    C2 psdt = ld2(F + FW_PS * lev);
+    if (q == 0) psdt = {0.0, 0.0};
+    // ---- B. spectral tendencies with time level 1 (tendencies.f90:283-352, alph = 0.5 branch of :31-38)
+    C2 d1[KX];
+#pragma unroll
+    for (int k = 0; k < KX; k++) d1[k] = ld2(dvs + k * lev);
+    C2 dmeanc = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KX; k++) dmeanc = dmeanc + d1[k] * c_T.dhs[k];
+    psdt = psdt - dmeanc;
+    if (q == 0) psdt = {0.0, 0.0};
+    {
+        C2 sig[KX + 1], dumk[KX + 1];
+        sig[0] = {0.0, 0.0}, sig[KX] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < KX - 1; k++) sig[k + 1] = sig[k] - c_T.dhs[k] * (d1[k] - dmeanc);
+        dumk[0] = {0.0, 0.0}, dumk[KX] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 1; k < KX; k++) dumk[k] = sig[k] * (c_T.tref[k] - c_T.tref[k - 1]);
+#pragma unroll
+        for (int k = 0; k < KX; k++)
+            tdt[k] = ((tdt[k] - (dumk[k + 1] + dumk[k]) * c_T.dhsr[k]) + c_T.tref3[k] * (sig[k + 1] + sig[k])) -
+                     c_T.tref2[k] * dmeanc;
+    }
+    const C2 ps1 = ld2(ps);
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        const C2 g = ld2(phi + k * lev) + (D_RGAS * c_T.tref[k]) * ps1;
+        divdt[k] = divdt[k] - ((-g) * el2);
+    }
+    // ---- C. semi-implicit correction (implicit.f90:234-289)
+    {
+        C2 yf[KX];
+        const double elz = I->elz[q];
+#pragma unroll
+        for (int k = 0; k < KX; k++) {
+            C2 ye = {0.0, 0.0};
+#pragma unroll
+            for (int k1 = 0; k1 < KX; k1++) ye = ye + I->xd[k + KX * k1] * tdt[k1];
+            ye = ye + (D_RGAS * c_T.tref[k]) * psdt;
+            yf[k] = divdt[k] + elz * ye;
+        }
+        const int l = m + n;
+#pragma unroll
+        for (int k = 0; k < KX; k++) divdt[k] = {0.0, 0.0};
+        if (l != 0) {
+            const double *xj = I->xj + (size_t)KX * KX * (l - 1);
+#pragma unroll
+            for (int k1 = 0; k1 < KX; k1++)
+#pragma unroll
+                for (int k = 0; k < KX; k++) divdt[k] = divdt[k] + xj[k + KX * k1] * yf[k1];
+        }
+#pragma unroll
+        for (int k = 0; k < KX; k++) psdt = psdt - divdt[k] * I->dhsx[k];
+#pragma unroll
+        for (int k = 0; k < KX; k++)
+#pragma unroll
+            for (int k1 = 0; k1 < KX; k1++) tdt[k] = tdt[k] + I->xc[k + KX * k1] * divdt[k1];
+    }
+    // ---- D/E. horizontal diffusion, stratospheric drag and time integration (time_stepping.f90:78-144)
+    const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
+    const double dmp1 = I->dmp1[q], dmp1d = I->dmp1d[q], dmp1s = I->dmp1s[q];
+    const double sdrag = 1.0 / ((double)(24.0f * 30.0f) * FL(3600.0));
+    const C2 tcorh = ld2(stp(c, t, c.off_tcorh, lane) + e), qcorh = ld2(stp(c, t, c.off_qcorh, lane) + e);
+    raw_update(ps, ps + lev, psdt, trf, j1, dt, eps, act);
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        const C2 v1 = ld2(vor + k * lev), t1 = ld2(tt + k * lev), q1 = ld2(trs + k * lev);
+        // vorticity tendency (spectral.f90:160-186 on utend, vtend)
+        C2 vo, dvx;
+        vdspec_elem(G, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, m, n, vo, dvx);
+        C2 dq, dumq;
+        vdspec_elem(G, F + (FW_UQ + k) * lev, F + (FW_VQ + k) * lev, m, n, dumq, dq);
+        C2 trdt = dq + ld2(F + (FW_QT + k) * lev);
+        C2 vordt = (vo - dmp * v1) * dmp1;
+        C2 dd = (divdt[k] - dmpd * d1[k]) * dmp1d;
+        const C2 ctmp = t1 + tcorh * c_T.tcorv[k];
+        C2 td = (tdt[k] - dmp * ctmp) * dmp1;
+        if (k == 0 && m == 0) {
+            vordt = vordt - sdrag * v1;
+            dd = dd - sdrag * d1[k];
+        }
+        vordt = (vordt - dmps * v1) * dmp1s;
+        dd = (dd - dmps * d1[k]) * dmp1s;
+        td = (td - dmps * ctmp) * dmp1s;
+        const C2 ctq = q1 + qcorh * c_T.qcorv[k];
+        trdt = (trdt - dmpd * ctq) * dmp1d;
+        raw_update(vor + k * lev, vor + tl + k * lev, vordt, trf, j1, dt, eps, act);
+        raw_update(dvs + k * lev, dvs + tl + k * lev, dd, trf, j1, dt, eps, act);
+        raw_update(tt + k * lev, tt + tl + k * lev, td, trf, j1, dt, eps, act);
+        raw_update(trs + k * lev, trs + tl + k * lev, trdt, trf, j1, dt, eps, act);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+// diagnostics.f90:16-74.  One warp per (tile, level); sums in the reference's order (m outer, n inner).
+__global__ void __launch_bounds__(32) k_diag(const Ctx c, const int time_lev) {
+    const int lane = threadIdx.x, k = blockIdx.x, t = blockIdx.y;
+    const size_t lev = (size_t)NSP * TILE, tl = (size_t)KX * lev * (time_lev - 1);
+    const double *vor = stp(c, t, c.off[V_vor], lane) + tl + k * lev, *dv = stp(c, t, c.off[V_div], lane) + tl + k * lev,
+                 *tt = stp(c, t, c.off[V_t], lane) + tl + k * lev;
+    const GlobTables *G = c.G;
+    double d1 = 0.0, d2 = 0.0;
+    for (int m = 1; m < MX; m++)
+        for (int n = 0; n < NX; n++) {
+            const size_t e = (size_t)(2 * m + M2 * n) * TILE;
+            const double em = G->elm2[m + MX * n];
+            const double vr = vor[e], vi = vor[e + TILE], dr = dv[e], di = dv[e + TILE];
+            const double ar = (-vr) * em, ai = (-vi) * em, br = (-dr) * em, bi = (-di) * em;
+            d1 = d1 - (ar * vr - ai * (-vi));
+            d2 = d2 - (br * dr - bi * (-di));
+        }
+    const double d3 = 0x1.6a09e6p-1 * tt[0];  // sqrt(0.5) REAL(4)
+    if (d1 > 500.0 || d2 > 500.0 || d3 < 180.0 || d3 > 320.0) slot(c, t, lane, SL_ERR) = -2.0;
+}
+
+// --------------------------------------------------------------------------------------------- member control
+// speedy.f90:41-53: per-member flags for this step
+__global__ void k_control_pre(const Ctx c) {
+    const int lane = threadIdx.x, t = blockIdx.x;
+    if (!lane_active(c, t, lane)) return;
+    const int step = (int)slot(c, t, lane, SL_STEP);
+    slot(c, t, lane, SL_ERR) = 0.0;
+    slot(c, t, lane, SL_DAILY) = (step % NSTEPS == 0) ? 1.0 : 0.0;
+    slot(c, t, lane, SL_SW) = (step % NSTRAD == 0) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ int days_in_month(int mth) {
+    const int d[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    return d[mth - 1];
+}
+// model_control.f90:166-186 (REAL(4) arithmetic)
+__device__ __forceinline__ void update_forcing_params(const Ctx &c, int t, int lane) {
+    const int month = (int)slot(c, t, lane, SL_MONTH), day = (int)slot(c, t, lane, SL_DAY);
+    int cum = 0;
+    for (int mm = 1; mm < month; mm++) cum += days_in_month(mm);
+    slot(c, t, lane, SL_IMONT1) = month;
+    slot(c, t, lane, SL_TMONTH) = (double)(((float)day - 0.5f) / (float)days_in_month(month));
+    slot(c, t, lane, SL_TYEAR) = (double)(((float)(cum + day) - 0.5f) / 365.0f);
+}
+// speedy.f90:59-69 + model_control.f90:113-163: step counter, then (if the check passed) the calendar
+__global__ void k_control_post(const Ctx c) {
+    const int lane = threadIdx.x, t = blockIdx.x;
+    if (!lane_active(c, t, lane)) return;
+    if (slot(c, t, lane, SL_ERR) != 0.0) return;
+    int year = (int)slot(c, t, lane, SL_YEAR), month = (int)slot(c, t, lane, SL_MONTH),
+        day = (int)slot(c, t, lane, SL_DAY), hour = (int)slot(c, t, lane, SL_HOUR),
+        minute = (int)slot(c, t, lane, SL_MINUTE), midx = (int)slot(c, t, lane, SL_MONTH_IDX);
+    minute += 24 * 60 / NSTEPS;
+    if (minute >= 60) minute %= 60, hour += 1;
+    if (hour >= 24) hour %= 24, day += 1;
+    if (year % 4 == 0 && month == 2) {
+        if (day > 29) day = 1, month += 1, midx += 1;
+    } else if (day > days_in_month(month)) {
+        day = 1, month += 1, midx += 1;
+    }
+    if (month > 12) month = 1, year += 1;
+    slot(c, t, lane, SL_YEAR) = year, slot(c, t, lane, SL_MONTH) = month, slot(c, t, lane, SL_DAY) = day;
+    slot(c, t, lane, SL_HOUR) = hour, slot(c, t, lane, SL_MINUTE) = minute, slot(c, t, lane, SL_MONTH_IDX) = midx;
+    update_forcing_params(c, t, lane);
+}
+__global__ void k_step_increment(const Ctx c) {
+    const int lane = threadIdx.x, t = blockIdx.x;
+    if (!lane_active(c, t, lane)) return;
+    slot(c, t, lane, SL_STEP) = slot(c, t, lane, SL_STEP) + 1.0;
+}
+__global__ void k_update_forcing_params(const Ctx c) {
+    const int lane = threadIdx.x, t = blockIdx.x;
+    if (lane_active(c, t, lane)) update_forcing_params(c, t, lane);
+}
+
+void launch_grid_dyn(cudaStream_t s, const Ctx &c, const ScratchLayout &L) {
+    k_grid_dyn<<<dim3(NG / 4, c.ntiles), 128, 0, s>>>(c, L);
+}
+void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j1, double dt, double eps, int impl_idx) {
+    k_spec_step<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+}
+void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, int) { k_diag<<<dim3(KX, c.ntiles), 32, 0, s>>>(c, time_lev); }
+void launch_control_pre(cudaStream_t s, const Ctx &c) { k_control_pre<<<c.ntiles, 32, 0, s>>>(c); }
+void launch_control_post(cudaStream_t s, const Ctx &c) { k_control_post<<<c.ntiles, 32, 0, s>>>(c); }
+void launch_step_increment(cudaStream_t s, const Ctx &c) { k_step_increment<<<c.ntiles, 32, 0, s>>>(c); }
+void launch_update_forcing_params(cudaStream_t s, const Ctx &c) { k_update_forcing_params<<<c.ntiles, 32, 0, s>>>(c); }
+
+}  // namespace spdy

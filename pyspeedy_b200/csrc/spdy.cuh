@@ -1,0 +1,119 @@
+// speedy-b200: common definitions for the CUDA hot path (sm_100a).
+//
+// DATA LAYOUT.  The ensemble lives in HBM as 32-member tiles ("ensemble-batched SoA"):
+//   element e of variable v of member (tile, lane):  arena[(tile * ELEMS + off[v] + e) * 32 + lane]
+// e is the Fortran linear index of the reference's ModelState_t array (model_state.f90, complex = re,im pair),
+// so every kernel is the reference's scalar code executed by lane = member: every load/store of a warp is one
+// contiguous 256-byte row, and all table look-ups are warp-uniform broadcasts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spdy_registry.h"
+
+namespace spdy {
+
+constexpr int TILE = 32;
+constexpr int MX = 31, NX = 32, KX = 8, IX = 96, IL = 48, IY = 24, NTRUNC = 30;
+constexpr int NSPC = MX * NX;       // 992 complex coefficients per spectral field
+constexpr int NSP = 2 * NSPC;       // 1984 doubles per spectral field (re,im interleaved; row = 2*MX = 62)
+constexpr int M2 = 2 * MX;          // 62
+constexpr int NG = IX * IL;         // 4608 grid points per level
+constexpr int NFOUR = M2 * IL;      // 2976 doubles per Fourier field (62 x 48)
+constexpr int NSTEPS = 36, NSTRAD = 3;
+
+// ---- per-member scalar slots (doubles; integers are stored exactly) -----------------------------------
+enum Slot {
+    SL_STEP = 0, SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE, SL_MONTH_IDX, SL_IMONT1, SL_TMONTH, SL_TYEAR,
+    SL_CO2, SL_CO2REF, SL_INCCO2, SL_SW, SL_LANDCPL, SL_SSTACPL, SL_ERR, SL_NMONTHS, SL_INITIALIZED, SL_DAILY,
+    SL_COUNT = 32
+};
+
+// ---- tables that are small and indexed with compile-time / warp-uniform indices: __constant__ -----------
+struct ConstTables {
+    double wa[96];   // FFTPACK twiddles (rffti1), 0-based
+    double fc[4];    // taui, sqrt2, hsqt2, fft scale (double)(1.f/96.f)
+    double hsg[KX + 1], dhs[KX], fsg[KX], dhsr[KX], fsgr[KX], sigl[KX], sigh[KX + 1], grdsig[KX], grdscp[KX];
+    double wvi[KX][2];
+    double tref[KX], tref2[KX], tref3[KX], tcorv[KX], qcorv[KX], xgeop1[KX], xgeop2[KX];
+    double coriol[IL], sia[IL], coa[IL], cosgr[IL], cosgr2[IL], radang[IL], wt[IY];
+    double geocorf[KX];  // lapse-rate correction factors of get_geopotential (k = 2..kx-1)
+};
+
+// ---- larger tables in global memory (warp-uniform loads) ---------------------------------------------------
+struct ImplTables {  // depends on the time step (implicit.f90:83-218): three instances dt/2, dt, 2dt
+    double dmp1[NSPC], dmp1d[NSPC], dmp1s[NSPC], elz[NSPC];
+    double xc[KX * KX], xd[KX * KX];  // (k,k1) Fortran order
+    double xj[KX * KX * 64];          // (k,k1,l)
+    double dhsx[KX];
+};
+struct GlobTables {
+    double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
+    double el2[NSPC], elm2[NSPC], trfilt[NSPC], gradym[NSPC], gradyp[NSPC], uvdx[NSPC], uvdym[NSPC], uvdyp[NSPC],
+        vddym[NSPC], vddyp[NSPC], dmp[NSPC], dmpd[NSPC], dmps[NSPC];
+    double gradx[MX];
+    double fband[301 * 4];
+    ImplTables impl[3];
+};
+
+__constant__ ConstTables c_T;  // unity build: single translation unit
+#define c_wa c_T.wa
+#define c_fc c_T.fc
+
+// ---- execution context passed by value to every kernel ----------------------------------------------------
+struct Ctx {
+    double *st;            // state arena
+    double *scr;           // scratch arena (chunk-local tiles)
+    double *sst;           // sst_anom arena
+    const int *tiles;      // [ntiles] state tile index of chunk tile t
+    const unsigned *masks; // [ntiles] active-lane mask
+    const GlobTables *G;
+    long long st_elems, scr_elems, sst_elems;  // doubles per lane per tile
+    long long off[SPDY_NVARS];                 // element offset of each registry variable
+    long long off_tcorh, off_qcorh, off_slots; // extra per-member state
+    int ntiles;
+    int sst_months;                            // slabs per member in the sst arena
+};
+
+__device__ __forceinline__ double *stp(const Ctx &c, int t, long long off, int lane) {
+    return c.st + ((long long)c.tiles[t] * c.st_elems + off) * TILE + lane;
+}
+__device__ __forceinline__ double *scp(const Ctx &c, int t, long long off, int lane) {
+    return c.scr + ((long long)t * c.scr_elems + off) * TILE + lane;
+}
+__device__ __forceinline__ bool lane_active(const Ctx &c, int t, int lane) { return (c.masks[t] >> lane) & 1u; }
+__device__ __forceinline__ double &slot(const Ctx &c, int t, int lane, int s) {
+    return *stp(c, t, c.off_slots + s, lane);
+}
+
+// A field reference: element offset inside a tile; bit 62 selects the scratch arena.
+typedef long long FieldRef;
+constexpr long long REF_SCR = 1ll << 62;
+__device__ __forceinline__ double *refp(const Ctx &c, int t, FieldRef r, int lane) {
+    return (r & REF_SCR) ? scp(c, t, r & ~REF_SCR, lane) : stp(c, t, r, lane);
+}
+
+// default-REAL literal widened to double, e.g. FL(0.05) == (double)0.05f
+#define FL(x) ((double)(x##f))
+
+// ---- scratch arena layout (element offsets; per lane) ------------------------------------------------------
+struct ScratchLayout {
+    // grid-point fields (NG * KX each unless noted)
+    long long ug, vg, tg, vorg, divg, trg;           // dynamics, time level j2
+    long long ptg, pqg, pphig, pug8, pvg8, pslg;    // physics, time level j1 (u,v: lowest level only)
+    long long px, py, psdtg;                         // 2-D
+    long long utend, vtend, ttend, trtend;
+    // spectral fields
+    long long ucos, vcos, ucosp8, vcosp8, dpx, dpy;  // inverse-transform inputs
+    long long sfwd;                                  // 73 forward-transform outputs
+    // Fourier fields (62 x 48)
+    long long four;                                  // max(77, 73) fields
+    long long total;
+};
+ScratchLayout make_scratch_layout();
+
+// forward-transform output slots inside `sfwd` (each NSP doubles): per level k = 0..7
+constexpr int FW_SU = 0, FW_SV = 8, FW_KE = 16, FW_UT = 24, FW_VT = 32, FW_TT = 40, FW_UQ = 48, FW_VQ = 56,
+              FW_QT = 64, FW_PS = 72, FW_COUNT = 73;
+
+}  // namespace spdy

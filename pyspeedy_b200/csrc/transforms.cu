@@ -1,0 +1,394 @@
+// speedy-b200: spectral transform kernels (Legendre + 96-point real FFT) and spectral-space operators.
+//
+// Reference semantics: legendre.f90:130-221, fourier.f90:63-123 (+ fftpack.f90), spectral.f90:134-296.
+// Layout: lane = ensemble member (32 per tile), see spdy.cuh.  All kernels: gridDim.y = chunk tiles.
+//
+//   k_legendre_inv : spectral (62x32) -> Fourier (62x48).  Per zonal wavenumber m a (24 x n) contraction; the
+//                    Legendre polynomial P(m,n,j) is warp-uniform (one 128-bit broadcast load feeds 2 j's for
+//                    32 members x {re,im}); register tile = 6 latitudes x {even,odd} x {re,im} = 24 accumulators.
+//   k_fft_inv      : Fourier -> grid, generated butterfly items (fft96_gen.cuh), 2 line-groups per CTA,
+//                    one shared-memory exchange between the two register stages.
+//   k_fft_fwd<M>   : grid -> Fourier with the grid-point products fused into the loads (M = loader mode).
+//   k_legendre_dir : Fourier -> spectral, Gaussian quadrature (fold N/S, weight, 24-term dot products).
+#include "kernels.h"
+
+namespace spdy {
+
+
+#define FFT_LS TILE
+#include "fft96_gen.cuh"
+
+// ------------------------------------------------------------------------------------------- Legendre inverse
+// One warp = one (field, m-pair); pairs (m, 30-m) balance the triangular truncation: 34 n-terms per pair.
+__device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, double *__restrict__ F,
+                                              const double *__restrict__ P, const int m0) {
+    const int nmax = 31 - m0;  // n0 = 0..nmax are inside the nsh2 mask (legendre.f90:68-77)
+    const double *Xr = X + (2 * m0) * TILE, *Xi = Xr + TILE;
+    const double *Pm = P + (size_t)m0 * NX * IY;
+#pragma unroll 1
+    for (int jt = 0; jt < 4; jt++) {
+        double er[6], ei[6], orr[6], oi[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) er[q] = ei[q] = orr[q] = oi[q] = 0.0;
+#pragma unroll 2
+        for (int n0 = 0; n0 <= nmax; n0 += 2) {  // even parity: l - m even
+            const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
+            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
+            const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
+            er[0] += xr * p0.x, ei[0] += xi * p0.x, er[1] += xr * p0.y, ei[1] += xi * p0.y;
+            er[2] += xr * p1.x, ei[2] += xi * p1.x, er[3] += xr * p1.y, ei[3] += xi * p1.y;
+            er[4] += xr * p2.x, ei[4] += xi * p2.x, er[5] += xr * p2.y, ei[5] += xi * p2.y;
+        }
+#pragma unroll 2
+        for (int n0 = 1; n0 <= nmax; n0 += 2) {  // odd parity
+            const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
+            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
+            const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
+            orr[0] += xr * p0.x, oi[0] += xi * p0.x, orr[1] += xr * p0.y, oi[1] += xi * p0.y;
+            orr[2] += xr * p1.x, oi[2] += xi * p1.x, orr[3] += xr * p1.y, oi[3] += xi * p1.y;
+            orr[4] += xr * p2.x, oi[4] += xi * p2.x, orr[5] += xr * p2.y, oi[5] += xi * p2.y;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const int j0 = jt * 6 + q, jn = IL - 1 - j0;  // legendre.f90:163-167: row il+1-j gets even+odd
+            double *fn = F + ((size_t)jn * M2 + 2 * m0) * TILE, *fs = F + ((size_t)j0 * M2 + 2 * m0) * TILE;
+            fn[0] = er[q] + orr[q], fn[TILE] = ei[q] + oi[q];
+            fs[0] = er[q] - orr[q], fs[TILE] = ei[q] - oi[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_legendre_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x >> 2, unit = (blockIdx.x & 3) * 4 + warp;  // 16 units per field
+    const int t = blockIdx.y;
+    const double *X = refp(c, t, descs[f].src, lane);
+    double *F = scp(c, t, four_off + (long long)f * NFOUR, lane);
+    const double *P = c.G->cpol;
+    if (unit < 15) {
+        leg_inv_one_m(X, F, P, unit);
+        leg_inv_one_m(X, F, P, 30 - unit);
+    } else {
+        leg_inv_one_m(X, F, P, 15);
+    }
+}
+
+// -------------------------------------------------------------------------------------------- Legendre direct
+__global__ void __launch_bounds__(128) k_legendre_dir(const Ctx c, const FwdOut *__restrict__ outs, long long four_off) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x >> 3, m0 = (blockIdx.x & 7) * 4 + warp;  // 32 slots, 31 used
+    const int t = blockIdx.y;
+    if (m0 >= MX) return;
+    const double *F = scp(c, t, four_off + (long long)f * NFOUR, lane);
+    double *X = refp(c, t, outs[f].dst, lane);
+    const double *Pm = c.G->cpol + (size_t)m0 * NX * IY;
+    const int nmax = min(30, 31 - m0);  // legendre.f90:206-218: n = 1..trunc+1 under the nsh2 mask
+#pragma unroll 1
+    for (int cc = 0; cc < 2; cc++) {
+        double ev[IY], od[IY];
+#pragma unroll
+        for (int j = 0; j < IY; j++) {  // legendre.f90:196-197
+            const double fs = F[((size_t)j * M2 + 2 * m0 + cc) * TILE];
+            const double fn = F[((size_t)(IL - 1 - j) * M2 + 2 * m0 + cc) * TILE];
+            ev[j] = (fn + fs) * c_T.wt[j];
+            od[j] = (fn - fs) * c_T.wt[j];
+        }
+#pragma unroll 1
+        for (int n0 = 0; n0 < NX; n0++) {
+            double acc = 0.0;
+            if (n0 <= nmax) {
+                const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY);
+                if ((n0 & 1) == 0) {
+#pragma unroll
+                    for (int j = 0; j < IY; j += 2) {
+                        const double2 pp = __ldg(p + (j >> 1));
+                        acc += pp.x * ev[j];
+                        acc += pp.y * ev[j + 1];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < IY; j += 2) {
+                        const double2 pp = __ldg(p + (j >> 1));
+                        acc += pp.x * od[j];
+                        acc += pp.y * od[j + 1];
+                    }
+                }
+            }
+            X[((size_t)n0 * M2 + 2 * m0 + cc) * TILE] = acc;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- inverse FFT
+// Static schedule of the 14 stage-A items (2 line-groups x 7) over 4 warps, balanced by flop count
+// (A0: 24, A1..A5: 96, A6: 36).  Entry = line_group * 8 + item ; 255 = none.
+__constant__ unsigned char c_schedA[4][4] = {
+    {0 * 8 + 1, 0 * 8 + 2, 0 * 8 + 3, 255},
+    {0 * 8 + 4, 0 * 8 + 5, 1 * 8 + 1, 255},
+    {1 * 8 + 2, 1 * 8 + 3, 0 * 8 + 0, 0 * 8 + 6},
+    {1 * 8 + 4, 1 * 8 + 5, 1 * 8 + 0, 1 * 8 + 6}};
+
+struct LdFour {
+    const double *p;
+    __device__ __forceinline__ double operator()(int r) const { return p[r * TILE]; }
+};
+struct StGrid {
+    double *p;
+    double sc;
+    __device__ __forceinline__ void operator()(int i, double v) const { p[i * TILE] = v * sc; }
+};
+
+__global__ void __launch_bounds__(128) k_fft_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off,
+                                                 int nlg) {
+    __shared__ double sm[2 * IX * TILE];  // 48 KB: exchange buffers of 2 line-groups
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.y, lg0 = blockIdx.x * 2;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int e = c_schedA[warp][r];
+        if (e == 255) continue;
+        const int g = e >> 3, item = e & 7, lg = lg0 + g;
+        if (lg >= nlg) continue;
+        const int f = lg / IL, j = lg - f * IL;
+        const LdFour ld{scp(c, t, four_off + (long long)f * NFOUR + j * M2, lane)};
+        double *s = sm + g * IX * TILE + lane;
+        switch (item) {
+            case 0: fftb_A0(ld, s); break;
+            case 1: fftb_A1(ld, s); break;
+            case 2: fftb_A2(ld, s); break;
+            case 3: fftb_A3(ld, s); break;
+            case 4: fftb_A4(ld, s); break;
+            case 5: fftb_A5(ld, s); break;
+            default: fftb_A6(ld, s); break;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int e = warp + 4 * r;  // 16 stage-B items
+        const int g = e >> 3, item = e & 7, lg = lg0 + g;
+        if (lg >= nlg) continue;
+        const int f = lg / IL, j = lg - f * IL;
+        const InvDesc d = descs[f];
+        const StGrid st{scp(c, t, d.dst + (long long)j * IX, lane), d.kcos == 1 ? 1.0 : c_T.cosgr[j]};
+        const double *s = sm + g * IX * TILE + lane;
+        switch (item) {
+            case 0: fftb_B0(s, st); break;
+            case 1: fftb_B1(s, st); break;
+            case 2: fftb_B2(s, st); break;
+            case 3: fftb_B3(s, st); break;
+            case 4: fftb_B4(s, st); break;
+            case 5: fftb_B5(s, st); break;
+            case 6: fftb_B6(s, st); break;
+            default: fftb_B7(s, st); break;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- forward FFT
+// Loader modes: the grid-point products of tendencies.f90:238-268 and the cos(lat) scalings of
+// spectral.f90:229-242 are applied while loading, so these fields never exist in HBM.
+template <int MODE> struct LdGrid {
+    const double *a, *b;
+    double k0, sc;
+    __device__ __forceinline__ double operator()(int i) const {
+        if (MODE == FM_PLAIN) return a[i * TILE];
+        if (MODE == FM_COS) return a[i * TILE] * sc;
+        if (MODE == FM_KE) {
+            const double u = a[i * TILE], v = b[i * TILE];
+            return 0.5 * (u * u + v * v);
+        }
+        if (MODE == FM_FLUXT) return (-a[i * TILE] * (b[i * TILE] - k0)) * sc;
+        return (-a[i * TILE] * b[i * TILE]) * sc;  // FM_FLUX
+    }
+};
+struct StFour {
+    double *p;
+    double scale;
+    __device__ __forceinline__ void operator()(int r, double v) const { p[r * TILE] = v * scale; }
+};
+
+// stage-B items of the forward transform: B0: 21, B1..B5: 102, B6: 34 flops ; 14 items over 4 warps
+__constant__ unsigned char c_schedFB[4][4] = {
+    {0 * 8 + 1, 0 * 8 + 2, 0 * 8 + 3, 255},
+    {0 * 8 + 4, 0 * 8 + 5, 1 * 8 + 1, 255},
+    {1 * 8 + 2, 1 * 8 + 3, 0 * 8 + 0, 0 * 8 + 6},
+    {1 * 8 + 4, 1 * 8 + 5, 1 * 8 + 0, 1 * 8 + 6}};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_fft_fwd(const Ctx c, const FwdDesc *__restrict__ descs, long long four_off,
+                                                 int nlg) {
+    __shared__ double sm[2 * IX * TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.y, lg0 = blockIdx.x * 2;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int e = warp + 4 * r;
+        const int g = e >> 3, item = e & 7, lg = lg0 + g;
+        if (lg >= nlg) continue;
+        const int f = lg / IL, j = lg - f * IL;
+        const FwdDesc d = descs[f];
+        LdGrid<MODE> ld;
+        ld.a = refp(c, t, d.a, lane) + (size_t)j * IX * TILE;
+        ld.b = (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) ? refp(c, t, d.b, lane) + (size_t)j * IX * TILE : nullptr;
+        ld.k0 = d.k0;
+        ld.sc = (d.kcos == 3) ? c_T.cosgr2[j] : c_T.cosgr[j];
+        double *s = sm + g * IX * TILE + lane;
+        switch (item) {
+            case 0: fftf_A0(ld, s); break;
+            case 1: fftf_A1(ld, s); break;
+            case 2: fftf_A2(ld, s); break;
+            case 3: fftf_A3(ld, s); break;
+            case 4: fftf_A4(ld, s); break;
+            case 5: fftf_A5(ld, s); break;
+            case 6: fftf_A6(ld, s); break;
+            default: fftf_A7(ld, s); break;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int e = c_schedFB[warp][r];
+        if (e == 255) continue;
+        const int g = e >> 3, item = e & 7, lg = lg0 + g;
+        if (lg >= nlg) continue;
+        const int f = lg / IL, j = lg - f * IL;
+        const FwdDesc d = descs[f];
+        double *four = scp(c, t, four_off + (long long)d.fidx * NFOUR + j * M2, lane);
+        const StFour st{four, c_T.fc[3]};
+        const double *s = sm + g * IX * TILE + lane;
+        switch (item) {
+            case 0: fftf_B0(s, st); four[TILE] = 0.0; break;  // item 0 owns row 0; Im(m=0) := 0, fourier.f90:117
+            case 1: fftf_B1(s, st); break;
+            case 2: fftf_B2(s, st); break;
+            case 3: fftf_B3(s, st); break;
+            case 4: fftf_B4(s, st); break;
+            case 5: fftf_B5(s, st); break;
+            default: fftf_B6(s, st); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ spectral-space pre-operators
+// uvspec (spectral.f90:190-214) for nlev levels, one warp per complex coefficient (m,n), lane = member
+__device__ __forceinline__ void uvspec_elem(const GlobTables *G, const double *vor, const double *dv, double *u,
+                                            double *v, int m, int n) {
+    const int q = m + MX * n;
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE, up = (size_t)M2 * TILE;
+    // zp = uvdx*vor*(0,1) ; zc = uvdx*div*(0,1)
+    const double ux = G->uvdx[q];
+    const double zpr = -(ux * vor[e + TILE]), zpi = ux * vor[e];
+    const double zcr = -(ux * dv[e + TILE]), zci = ux * dv[e];
+    if (n == 0) {
+        const double yp = G->uvdyp[q];
+        u[e] = zcr - yp * vor[e + up], u[e + TILE] = zci - yp * vor[e + up + TILE];
+        v[e] = zpr + yp * dv[e + up], v[e + TILE] = zpi + yp * dv[e + up + TILE];
+    } else if (n == NX - 1) {
+        const double ym = G->uvdym[q];
+        u[e] = ym * vor[e - up], u[e + TILE] = ym * vor[e - up + TILE];
+        v[e] = -ym * dv[e - up], v[e + TILE] = -ym * dv[e - up + TILE];
+    } else {
+        const double ym = G->uvdym[q], yp = G->uvdyp[q];
+        v[e] = (-ym * dv[e - up] + yp * dv[e + up]) + zpr;
+        v[e + TILE] = (-ym * dv[e - up + TILE] + yp * dv[e + up + TILE]) + zpi;
+        u[e] = (ym * vor[e - up] - yp * vor[e + up]) + zcr;
+        u[e + TILE] = (ym * vor[e - up + TILE] - yp * vor[e + up + TILE]) + zci;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const double *pv = refp(c, t, vor, lane), *pd = refp(c, t, dv, lane);
+    double *pu = refp(c, t, u, lane), *pw = refp(c, t, v, lane);
+    for (int k = 0; k < nlev; k++)
+        uvspec_elem(c.G, pv + (size_t)k * NSP * TILE, pd + (size_t)k * NSP * TILE, pu + (size_t)k * NSP * TILE,
+                    pw + (size_t)k * NSP * TILE, m, n);
+}
+
+// gradient (spectral.f90:275-296)
+__global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, FieldRef dx, FieldRef dy) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const GlobTables *G = c.G;
+    const double *p = refp(c, t, psi, lane);
+    double *px = refp(c, t, dx, lane), *py = refp(c, t, dy, lane);
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE, up = (size_t)M2 * TILE;
+    const double gx = G->gradx[m];
+    px[e] = -(gx * p[e + TILE]);
+    px[e + TILE] = gx * p[e];
+    if (n == 0) {
+        py[e] = G->gradyp[q] * p[e + up], py[e + TILE] = G->gradyp[q] * p[e + up + TILE];
+    } else if (n == NX - 1) {
+        py[e] = -G->gradym[q] * p[e - up], py[e + TILE] = -G->gradym[q] * p[e - up + TILE];
+    } else {
+        py[e] = -G->gradym[q] * p[e - up] + G->gradyp[q] * p[e + up];
+        py[e + TILE] = -G->gradym[q] * p[e - up + TILE] + G->gradyp[q] * p[e + up + TILE];
+    }
+}
+
+// geopotential (geopotential.f90:36-77): phi from T(time level) and phis ; one warp per coefficient
+__global__ void __launch_bounds__(128) k_geopotential(const Ctx c, FieldRef tref_, FieldRef phis, FieldRef phi) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE, lev = (size_t)NSP * TILE;
+    const double *T = refp(c, t, tref_, lane) + e, *ps = refp(c, t, phis, lane) + e;
+    double *ph = refp(c, t, phi, lane) + e;
+    const bool act = lane_active(c, t, lane);
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+        double tk[KX], p[KX];
+#pragma unroll
+        for (int k = 0; k < KX; k++) tk[k] = T[k * lev + cc * TILE];
+        p[KX - 1] = ps[cc * TILE] + c_T.xgeop1[KX - 1] * tk[KX - 1];
+#pragma unroll
+        for (int k = KX - 2; k >= 0; k--) p[k] = (p[k + 1] + c_T.xgeop2[k + 1] * tk[k + 1]) + c_T.xgeop1[k] * tk[k];
+        if (m == 0) {
+#pragma unroll
+            for (int k = 1; k < KX - 1; k++) p[k] = p[k] + c_T.geocorf[k] * (tk[k + 1] - tk[k - 1]);
+        }
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < KX; k++) ph[k * lev + cc * TILE] = p[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- launchers
+void launch_legendre_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off) {
+    if (nf) k_legendre_inv<<<dim3(nf * 4, c.ntiles), 128, 0, s>>>(c, d, four_off);
+}
+void launch_fft_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off) {
+    const int nlg = nf * IL;
+    if (nf) k_fft_inv<<<dim3((nlg + 1) / 2, c.ntiles), 128, 0, s>>>(c, d, four_off, nlg);
+}
+void launch_fft_fwd(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, int nf, long long four_off) {
+    if (!nf) return;
+    const int nlg = nf * IL;
+    const dim3 g((nlg + 1) / 2, c.ntiles);
+    switch (mode) {
+        case FM_PLAIN: k_fft_fwd<FM_PLAIN><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_COS: k_fft_fwd<FM_COS><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_KE: k_fft_fwd<FM_KE><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_FLUXT: k_fft_fwd<FM_FLUXT><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        default: k_fft_fwd<FM_FLUX><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+    }
+}
+void launch_legendre_dir(cudaStream_t s, const Ctx &c, const FwdOut *o, int nf, long long four_off) {
+    if (nf) k_legendre_dir<<<dim3(nf * 8, c.ntiles), 128, 0, s>>>(c, o, four_off);
+}
+void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev) {
+    k_uvspec<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, vor, dv, u, v, nlev);
+}
+void launch_gradient(cudaStream_t s, const Ctx &c, FieldRef psi, FieldRef dx, FieldRef dy) {
+    k_gradient<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, psi, dx, dy);
+}
+void launch_geopotential(cudaStream_t s, const Ctx &c, FieldRef tlev, FieldRef phis, FieldRef phi) {
+    k_geopotential<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, tlev, phis, phi);
+}
+void upload_const_tables(const ConstTables &C) { cudaMemcpyToSymbol(c_T, &C, sizeof(C)); }
+
+}  // namespace spdy

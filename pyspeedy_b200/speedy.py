@@ -1,0 +1,340 @@
+"""The Speedy model classes: host-side mirror of pyspeedy/speedy.py (same names, arguments and error behaviour).
+
+Differences, all forced by this image (no xarray / netCDF4 / HDF5) and documented in DESIGN.md:
+  * boundary conditions are read from ``.npz`` files with the reference's variable names (``tools/convert_reference_data.py``
+    converts the reference's example_bc.nc); NetCDF input is used when xarray is importable;
+  * the default SST anomaly file is not available: a zero anomaly of the right length is used unless
+    ``sst_anomaly`` is given (an ``.npz`` with ``ssta`` (lon, lat, time) and ``time`` as ``YYYY-MM`` strings, or an
+    array);
+  * ``to_dataframe`` returns ``xarray.Dataset`` when xarray is importable, else :class:`pyspeedy_b200.dataset.Dataset`
+    (same dims/ordering/dtypes, NetCDF-3 writer).
+Ensemble extension: ``SpeedyEns.run(..., steps_per_call=n)`` advances all members ``n`` steps per driver call.
+"""
+import json
+import os
+from datetime import datetime, timedelta
+
+import numpy as np
+
+from pyspeedy_b200 import (
+    _speedy,  # noqa
+    example_bc_file,
+    example_sst_anomaly_file,
+    PACKAGE_DATA_DIR,
+    DEFAULT_OUTPUT_VARS,
+)
+from pyspeedy_b200.dataset import Dataset
+from pyspeedy_b200.error_codes import ERROR_CODES
+
+with open(PACKAGE_DATA_DIR / "model_state.json") as fp:
+    MODEL_STATE_DEF = {e["name"]: e for e in json.load(fp)}
+
+# boundary-condition file variable -> state variable (pyspeedy/speedy.py:279-296)
+_BC_VARS = (
+    ("orog", "orog"), ("fmask_orig", "lsm"), ("alb0", "alb"), ("veg_high", "vegh"), ("veg_low", "vegl"),
+    ("stl12", "stl"), ("snowd12", "snowd"), ("soil_wc_l1", "swl1"), ("soil_wc_l2", "swl2"), ("soil_wc_l3", "swl3"),
+    ("sst12", "sst"), ("sea_ice_frac12", "icec"),
+)
+
+
+def _add_months(date, months):
+    y, m = divmod(date.year * 12 + (date.month - 1) + months, 12)
+    return date.replace(year=y, month=m + 1)
+
+
+def _load_bc(bc_file):
+    if bc_file.endswith(".npz"):
+        with np.load(bc_file) as f:
+            return {k: f[k] for k in f.files}
+    try:
+        import xarray as xr
+    except ImportError as exc:  # pragma: no cover
+        raise RuntimeError("NetCDF boundary files need xarray + netCDF4; use an .npz file in this image.") from exc
+    ds = xr.load_dataset(bc_file, engine="netcdf4")
+    return {k: ds[k].values for k in ds.data_vars}
+
+
+class Speedy:
+    """Speedy model (one ensemble member resident on the GPU)."""
+
+    def __init__(self, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2), member=None):
+        self._start_date = None
+        self._end_date = None
+        self._model_date = None
+        self._control_cnt = None
+        self.member_id = member
+        self.is_ensemble_member = self.member_id is not None
+        self._state_cnt = _speedy.modelstate_init()
+        self.set_params(start_date=start_date, end_date=end_date)
+        self._initialized_bc = False
+        self._initialized_ssta = False
+        self.current_date = self.start_date
+
+    def __del__(self):
+        try:
+            _speedy.modelstate_close(self._state_cnt)
+            _speedy.controlparams_close(self._control_cnt)
+            self._dealloc_date(self._start_date)
+            self._dealloc_date(self._end_date)
+        except Exception:  # interpreter shutdown
+            pass
+
+    def set_params(self, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)):
+        self.start_date = start_date
+        self.end_date = end_date
+        if self.start_date > self.end_date:
+            raise ValueError("The start date should be lower than the en date.")
+        self._control_cnt = _speedy.controlparams_init(self._start_date, self._end_date)
+        self._model_date = None
+        self.current_date = start_date
+        self.n_months = (
+            (self.end_date.year - self.start_date.year) * 12 + (self.end_date.month - self.start_date.month) + 1
+        )
+
+    @staticmethod
+    def _dealloc_date(container):
+        if container is not None:
+            _speedy.close_datetime(container)
+
+    def __getitem__(self, var_name):
+        _getter = getattr(_speedy, f"get_{var_name}", None)
+        if _getter is None:
+            raise AttributeError(f"The state variable '{var_name}' does not exist.")
+        time_dim = MODEL_STATE_DEF[var_name]["time_dim"]
+        if time_dim:
+            return _getter(self._state_cnt, getattr(self, time_dim))
+        return _getter(self._state_cnt)
+
+    def get_shape(self, var_name):
+        _getter = getattr(_speedy, f"get_{var_name}_shape", None)
+        if _getter is None:
+            raise AttributeError(f"The 'get-shape' method for the state variable {var_name}' does not exist.")
+        return tuple(int(x) for x in _getter(self._state_cnt))
+
+    def __setitem__(self, var_name, value):
+        _setter = getattr(_speedy, f"set_{var_name}", None)
+        if _setter is None:
+            raise AttributeError(f"The setter for the state variable '{var_name}' does not exist.")
+        is_array_func = getattr(_speedy, f"is_array_{var_name}")
+        if is_array_func():
+            value = np.asarray(value)
+            if self.get_shape(var_name) != value.shape:
+                raise ValueError("Array shape missmatch")
+            value = np.asfortranarray(value)
+            time_dim = MODEL_STATE_DEF[var_name]["time_dim"]
+            if time_dim:
+                return _setter(self._state_cnt, value, getattr(self, time_dim))
+            return _setter(self._state_cnt, value)
+        return _setter(self._state_cnt, value)
+
+    @staticmethod
+    def _get_fortran_date(container):
+        return datetime(*_speedy.get_datetime(container))
+
+    @staticmethod
+    def _set_fortran_date(container, date_value):
+        Speedy._dealloc_date(container)
+        if isinstance(date_value, datetime):
+            return _speedy.create_datetime(
+                date_value.year, date_value.month, date_value.day, date_value.hour, date_value.minute
+            )
+        raise TypeError("The input value is not a datetime object.")
+
+    def get_current_step(self):
+        return self["current_step"]
+
+    @property
+    def start_date(self):
+        return self._get_fortran_date(self._start_date)
+
+    @start_date.setter
+    def start_date(self, value):
+        self._start_date = self._set_fortran_date(self._start_date, value)
+
+    @property
+    def current_date(self):
+        return self._get_fortran_date(self._model_date)
+
+    @current_date.setter
+    def current_date(self, value):
+        self._model_date = self._set_fortran_date(self._model_date, value)
+
+    @property
+    def end_date(self):
+        return self._get_fortran_date(self._end_date)
+
+    @end_date.setter
+    def end_date(self, value):
+        self._end_date = self._set_fortran_date(self._end_date, value)
+
+    def set_bc(self, bc_file=None, sst_anomaly=None):
+        """Set the boundary conditions and initialise the model (pyspeedy/speedy.py:217-301)."""
+        if self._initialized_bc:
+            raise RuntimeError(
+                "The model was already initialized. Create a new instance if you need different boundary conditions."
+            )
+        self._set_sst_anomalies(sst_anomaly=sst_anomaly)
+        if bc_file is None:
+            bc_file = example_bc_file()
+        if not os.path.isfile(bc_file):
+            raise RuntimeError("The boundary conditions file does not exist.\n" f"File: {bc_file}")
+        ds = _load_bc(bc_file)
+        for var, key in _BC_VARS:
+            self[var] = np.asarray(ds[key], dtype=np.float64)
+        error_code = _speedy.init(self._state_cnt, self._control_cnt)
+        if error_code < 0:
+            raise RuntimeError(ERROR_CODES[error_code])
+        self.spectral2grid()
+        self._initialized_bc = True
+
+    def _set_sst_anomalies(self, sst_anomaly=None):
+        """Load the SST anomalies for the 3-month window around the run (pyspeedy/speedy.py:303-373)."""
+        if self._initialized_ssta:
+            raise RuntimeError(
+                "The SST anomaly was already initialized."
+                " Create a new instance if you need different boundary conditions."
+            )
+        start_date = _add_months(self.start_date.replace(day=1, hour=0, minute=0, microsecond=0), -1)
+        end_date = _add_months(self.end_date.replace(day=1, hour=0, minute=0, microsecond=0), 1)
+        expected_months = (end_date.year - start_date.year) * 12 + (end_date.month - start_date.month) + 1
+        if sst_anomaly is None and os.path.isfile(example_sst_anomaly_file()):
+            sst_anomaly = example_sst_anomaly_file()
+        if sst_anomaly is None:
+            ssta = np.zeros((96, 48, expected_months))  # documented deviation: default anomaly file unavailable
+        elif isinstance(sst_anomaly, str):
+            if not os.path.isfile(sst_anomaly):
+                raise RuntimeError("The SST anomaly file does not exist.\n" f"File: {sst_anomaly}")
+            with np.load(sst_anomaly) as f:
+                months = [str(m) for m in f["time"]]
+                wanted = [_add_months(start_date, i).strftime("%Y-%m") for i in range(expected_months)]
+                missing = [w for w in wanted if w not in months]
+                if missing:
+                    raise RuntimeError(
+                        f"{len(missing)} months are missing in the SST anomalies file for the period: "
+                        + start_date.strftime("%Y/%m/%d") + " , " + end_date.strftime("%Y/%m/%d") + ".\n "
+                    )
+                ssta = np.stack([f["ssta"][:, :, months.index(w)] for w in wanted], axis=-1)
+        elif isinstance(sst_anomaly, np.ndarray):
+            ssta = sst_anomaly
+            if ssta.shape != (96, 48, expected_months):
+                raise RuntimeError(f"{expected_months} months of SST anomalies are needed, got shape {ssta.shape}")
+        else:
+            raise TypeError(f"Unsupported sst_anomaly input: {type(sst_anomaly)}")
+        _speedy.modelstate_init_sst_anom(self._state_cnt, expected_months - 2)
+        self["sst_anom"] = np.asarray(ssta, dtype=np.float64)
+        self._initialized_ssta = True
+
+    def run(self, callbacks=None):
+        """Run the model between the start and end dates (pyspeedy/speedy.py:375-405)."""
+        if callbacks is None:
+            callbacks = list()
+        if not self._initialized_bc:
+            raise RuntimeError("The SPEEDY model was not initialized. Call the `set_bc` method to initialize the model.")
+        self.current_date = self.start_date
+        dt_step = timedelta(seconds=3600 * 24 / 36)
+        while self.current_date < self.end_date:
+            error_code = _speedy.step(self._state_cnt, self._control_cnt)
+            if error_code < 0:
+                raise RuntimeError(ERROR_CODES[error_code])
+            self.current_date += dt_step
+            for callback in callbacks:
+                callback(self)
+
+    def grid2spectral(self):
+        _speedy.transform_grid2spectral(self._state_cnt)
+
+    def spectral2grid(self):
+        _speedy.transform_spectral2grid(self._state_cnt)
+
+    def grid_filter(self):
+        _speedy.apply_grid_filter(self._state_cnt)
+
+    def to_dataframe(self, variables=None):
+        """Dataset with the current model state: dims (time[, ens], lev, lat, lon), float32, levels increasing
+        with height (pyspeedy/speedy.py:415-477)."""
+        if variables is None:
+            variables = DEFAULT_OUTPUT_VARS
+        self.spectral2grid()
+        data_vars = dict()
+        attrs = dict()
+        for var in variables:
+            dims = list(MODEL_STATE_DEF[var]["nc_dims"]) + ["time"]
+            var_data = self[var][..., None].astype("float32")
+            if self.is_ensemble_member:
+                dims = dims + ["ens"]
+                var_data = var_data[..., None]
+            name = MODEL_STATE_DEF[var]["alt_name"]
+            data_vars[name] = (dims, var_data)
+            attrs[name] = dict(long_name=MODEL_STATE_DEF[var]["desc"], standard_name=MODEL_STATE_DEF[var]["std_name"])
+            if MODEL_STATE_DEF[var]["units"] is not None:
+                attrs[name]["units"] = MODEL_STATE_DEF[var]["units"]
+        coords = dict(lon=self["lon"], lat=self["lat"], lev=self["lev"], time=[self.current_date])
+        if self.is_ensemble_member:
+            coords["ens"] = [self.member_id]
+        ds = Dataset(data_vars=data_vars, coords=coords, attrs=attrs)
+        sorted_dims = ("time", "ens", "lev", "lat", "lon") if self.is_ensemble_member else ("time", "lev", "lat", "lon")
+        ds = ds.reverse("lev").transpose(*sorted_dims)
+        return ds.to_xarray() if Dataset.HAVE_XARRAY else ds
+
+    def check(self):
+        error_code = _speedy.check(self._state_cnt)
+        if error_code < 0:
+            raise RuntimeError(ERROR_CODES[error_code])
+
+
+class SpeedyEns:
+    """Ensemble of Speedy model instances, advanced together by one driver call per step."""
+
+    def __init__(self, num_of_members, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)):
+        self.n_members = num_of_members
+        self.members = [Speedy(start_date=start_date, end_date=end_date, member=n) for n in range(num_of_members)]
+        self.current_date = self.members[0].current_date
+
+    def __iter__(self):
+        return iter(self.members)
+
+    def __len__(self):
+        return self.n_members
+
+    def set_params(self, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)):
+        for member in self:
+            member.set_params(start_date=start_date, end_date=end_date)
+        self.current_date = start_date
+
+    def to_dataframe(self, variables=None):
+        return Dataset.merge([member.to_dataframe(variables=variables) for member in self])
+
+    def run(self, callbacks=None, steps_per_call=1):
+        """Run every member between the start and end dates (pyspeedy/speedy.py:547-593).
+
+        ``steps_per_call > 1`` (extension) keeps the time loop on the device between callbacks."""
+        if callbacks is None:
+            callbacks = []
+        end_date = self.members[0].end_date
+        dt_step = timedelta(seconds=3600 * 24 / 36)
+        state_cnts = np.zeros(self.n_members, dtype=np.int64)
+        control_cnts = np.zeros(self.n_members, dtype=np.int64)
+        for m, member in enumerate(self):
+            state_cnts[m] = member._state_cnt  # noqa
+            control_cnts[m] = member._control_cnt  # noqa
+        while self.current_date < end_date:
+            if steps_per_call > 1:
+                left = int(round((end_date - self.current_date) / dt_step))
+                n = max(1, min(steps_per_call, left))
+                error_codes = _speedy.run_steps(state_cnts, control_cnts, n)
+                self.current_date += n * dt_step
+            else:
+                error_codes = _speedy.parallel_step(state_cnts, control_cnts)
+                self.current_date += dt_step
+            if (error_codes < 0).any():
+                msg = ""
+                for n, code in enumerate(error_codes):
+                    msg += f"Member{n}: {ERROR_CODES[code]}\n"
+                raise RuntimeError(msg)
+            for member in self:
+                member.current_date = self.current_date
+            for callback in callbacks:
+                callback(self)
+
+    def get_current_step(self):
+        return self.members[0]["current_step"]

@@ -1,0 +1,93 @@
+"""Column physics kernel vs the oracle on synthetic columns (BASELINE config 5 distributions), both short-wave
+phases; integer diagnostics (itop, icnv, icltop) must agree exactly."""
+import ctypes as C
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+from util import ptr, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def synth_columns(st, seed=7):
+    """T = reference profile + N(0,5K); ps/p0 ~ U(0.5,1.05); rh ~ U(0,1.1); u,v ~ N(0,10); hydrostatic phi."""
+    rng = np.random.default_rng(seed)
+    fsg = np.array([0.025, 0.095, 0.2, 0.34, 0.51, 0.685, 0.835, 0.95])
+    tref = 288.0 * np.maximum(0.2, fsg) ** (287.0 * 0.006 / 9.81)
+    tg = tref[None, None, :] + rng.normal(0, 5.0, size=(96, 48, 8))
+    psa = rng.uniform(0.5, 1.05, size=(96, 48))
+    pslg = np.log(psa)
+    e0, c1, c2, t0, t1, t2 = 6.108e-3, 17.269, 21.875, 273.16, 35.86, 7.66
+    qs = np.where(tg >= t0, e0 * np.exp(c1 * (tg - t0) / (tg - t1)), e0 * np.exp(c2 * (tg - t0) / (tg - t2)))
+    qs = 622.0 * qs / (fsg[None, None, :] * psa[:, :, None] - 0.378 * qs)
+    qg = rng.uniform(0, 1.1, size=(96, 48, 8)) * qs
+    ug = rng.normal(0, 10, size=(96, 48, 8))
+    vg = rng.normal(0, 10, size=(96, 48, 8))
+    phis0 = np.maximum(0.0, rng.normal(0, 5e3, size=(96, 48)))
+    hsg = np.array([0.0, 0.05, 0.14, 0.26, 0.42, 0.6, 0.77, 0.9, 1.0])
+    phig = np.zeros((96, 48, 8))
+    phig[:, :, 7] = phis0 + 287.0 * np.log(hsg[8] / fsg[7]) * tg[:, :, 7]
+    for k in range(6, -1, -1):
+        phig[:, :, k] = phig[:, :, k + 1] + 287.0 * np.log(fsg[k + 1] / fsg[k]) * 0.5 * (tg[:, :, k] + tg[:, :, k + 1])
+    surf = dict(phis0=phis0, fmask_land=rng.choice([0.0, 1.0, 0.37], size=(96, 48)), forog=rng.uniform(1, 1.5, (96, 48)),
+                sst_am=rng.uniform(271, 303, (96, 48)), land_temp=rng.uniform(230, 310, (96, 48)),
+                alb_land=rng.uniform(0.07, 0.6, (96, 48)), alb_sea=rng.uniform(0.07, 0.6, (96, 48)),
+                alb_surface=rng.uniform(0.07, 0.6, (96, 48)), soil_avail_water=rng.uniform(0, 1, (96, 48)),
+                snowc=rng.uniform(0, 1, (96, 48)), ssrd=rng.uniform(0, 300, (96, 48)))
+    F = lambda a: np.asfortranarray(a)
+    return [F(x) for x in (ug, vg, tg, qg, phig, pslg)], surf
+
+
+@pytest.mark.parametrize("sw", [True, False])
+def test_physics_columns(oracle, drv, sw):
+    from pyspeedy_b200 import Speedy
+
+    st = oracle.State(n_months=1)
+    st.init_tables()
+    st.zonal_average_fields(0.03)
+    m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    (ug, vg, tg, qg, phig, pslg), surf = synth_columns(st)
+    for k, v in surf.items():
+        st[k] = v
+    rng = np.random.default_rng(3)
+    for name in ("flux_solar_in", "flux_ozone_lower", "flux_ozone_upper", "zenit_correction", "stratospheric_correction"):
+        surf[name] = st[name]
+    if not sw:  # persisted short-wave state from a previous step
+        surf["rad_tau2"] = rng.uniform(0.3, 1.0, (96, 48, 8, 4))
+        surf["tt_rsw"] = rng.uniform(0, 1e-5, (96, 48, 8))
+        surf["rad_strat_corr"] = rng.uniform(0, 5, (96, 48, 2))
+        for k in ("rad_tau2", "tt_rsw", "rad_strat_corr"):
+            st[k] = surf[k]
+    for k, v in surf.items():
+        m[k] = v
+    st["compute_shortwave"] = int(sw)
+    m["compute_shortwave"] = int(sw)
+    tend = [np.asfortranarray(rng.normal(0, 1e-5, (96, 48, 8))) for _ in range(4)]
+    o_t = [a.copy(order="F") for a in tend]
+    qg_o = qg.copy(order="F")
+    dbg_o = st.physics_columns(ug, vg, tg, qg_o, phig, pslg, *o_t)
+    u8, v8 = np.ascontiguousarray(ug[:, :, 7].T).T.copy(order="F"), vg[:, :, 7].copy(order="F")
+    g_u8, g_v8 = tend[0][:, :, 7].copy(order="F"), tend[1][:, :, 7].copy(order="F")
+    g_t, g_q = tend[2].copy(order="F"), tend[3].copy(order="F")
+    dbg = np.zeros((3, 48, 96), dtype=np.int32)
+    rc = drv.lib().spdy_debug_physics(m._state_cnt, ptr(u8), ptr(v8), ptr(tg), ptr(qg), ptr(phig), ptr(pslg),
+                                      ptr(g_u8), ptr(g_v8), ptr(g_t), ptr(g_q), ptr(dbg))
+    assert rc == 0
+    assert np.array_equal(dbg[0], dbg_o[0]), "itop"
+    assert np.array_equal(dbg[1], dbg_o[1]), "icnv"
+    if sw:
+        assert np.array_equal(dbg[2], dbg_o[2]), "icltop"
+    assert relerr(g_u8, o_t[0][:, :, 7]) < 1e-12
+    assert relerr(g_v8, o_t[1][:, :, 7]) < 1e-12
+    assert relerr(g_t, o_t[2]) < 1e-12
+    assert relerr(g_q, o_t[3]) < 1e-12
+    # levels 1..7 of the wind tendencies are untouched by the physics (physics.f90:214-221)
+    assert np.array_equal(o_t[0][:, :, :7], tend[0][:, :, :7])
+    for v in ["precnv", "precls", "cbmf", "slrd", "slr", "olr", "slru", "ustr", "vstr", "shf", "evap", "hfluxn",
+              "rad_flux", "rad_st4a"] + (["tsr", "ssrd", "ssr", "tt_rsw", "rad_tau2", "rad_strat_corr", "qcloud_equiv"] if sw else []):
+        a, b = m[v], st[v]
+        if v == "hfluxn":
+            a, b = a[:, :, :2], b[:, :, :2]
+        assert relerr(a, b) < 1e-12, (v, relerr(a, b))

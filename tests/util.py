@@ -1,0 +1,29 @@
+"""Shared helpers of the parity tests."""
+import ctypes as C
+
+import numpy as np
+
+MX, NX, KX, IX, IL = 31, 32, 8, 96, 48
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def synth_spec(n, seed=2024, scale=1.0):
+    """BASELINE config 4: N(0,1)*(1+l)^-1 inside l <= 30, zero outside, Im(m=0) = 0.  Shape (n, 32, 31) complex
+    (C order = Fortran (31, 32) per field)."""
+    rng = np.random.default_rng(seed)
+    m = np.arange(MX)[None, :]
+    nn = np.arange(NX)[:, None]
+    l = m + nn
+    amp = np.where(l <= 30, 1.0 / (1.0 + l), 0.0)
+    x = (rng.standard_normal((n, NX, MX)) + 1j * rng.standard_normal((n, NX, MX))) * amp * scale
+    x[:, :, 0] = x[:, :, 0].real
+    return np.ascontiguousarray(x)
+
+
+def relerr(a, b):
+    """max |a-b| / max |b| -- the norm the parity tolerances are stated in."""
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
