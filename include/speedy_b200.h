@@ -64,6 +64,16 @@ int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const doub
 int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **sum_sumsq_dev,
                               size_t *nelem);
 
+/* copy the complete device state of `src` into every member of `dst` (ensemble set-up from one initialised member) */
+int spdy_clone_state(int64_t src, const int64_t *dst, int n);
+/* t_grid += N(0,sigma) per grid point, then grid2spectral of T (examples/Ensemble_forecast.ipynb cell 8) for all listed
+ * members, on the device, with a counter-based generator seeded per (member, point, level) */
+int spdy_perturb_temperature(const int64_t *states, int n, unsigned long long seed, double sigma);
+int spdy_batch_spectral2grid(const int64_t *states, int n);      /* transform_spectral2grid for a member list */
+/* one step with CUDA events between kernel classes: ms[10] = forcing, pre-ops, legendre_inv, fft_inv, grid_dyn,
+ * physics, fft_fwd, legendre_dir, spec_step, post (first chunk of 16 tiles is instrumented) */
+int spdy_profile_step(const int64_t *states, const int64_t *controls, int n, float *ms, int *error_codes);
+
 /* ---- stage-level entry points (parity tests, microbenchmarks); host buffers, one field after another -------- */
 int spdy_table(const char *name, double *dst, int cap);
 int spdy_batch_spec2grid(const double *spec /* n x (31,32) complex */, double *grid /* n x (96,48) */, int kcos, int n);

@@ -28,6 +28,13 @@ size_t var_count(const State &s, int v) { return s.var[v].size(); }
 extern "C" {
 
 void *orc_state_create() { return new State(); }
+void *orc_state_clone(void *p) {
+    State *s = new State(*(State *)p);
+    s->spec.geo = &s->geo;  // re-point the module back-references of the copy
+    s->imp.geo = &s->geo;
+    return s;
+}
+void *orc_control_clone(void *p) { return new Control(*(Control *)p); }
 void orc_state_destroy(void *p) { delete (State *)p; }
 void orc_alloc_sst_anom(void *p, int n_months) { ((State *)p)->alloc_sst_anom(n_months); }
 

@@ -38,6 +38,10 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.orc_state_create.restype = C.c_void_p
         L.orc_control_create.restype = C.c_void_p
+        L.orc_state_clone.restype = C.c_void_p
+        L.orc_state_clone.argtypes = [C.c_void_p]
+        L.orc_control_clone.restype = C.c_void_p
+        L.orc_control_clone.argtypes = [C.c_void_p]
         L.orc_control_create.argtypes = [C.c_void_p, C.c_void_p]
         for name in ("orc_state_destroy", "orc_control_destroy", "orc_spectral2grid", "orc_grid2spectral",
                      "orc_grid_filter", "orc_state_init_tables", "orc_advance_date"):
@@ -191,6 +195,11 @@ class Control:
             lib().orc_control_destroy(C.c_void_p(self.h))
             self.h = None
 
+    def clone(self):
+        c = Control.__new__(Control)
+        c.h = lib().orc_control_clone(C.c_void_p(self.h))
+        return c
+
     @property
     def date(self):
         out = np.zeros(5, dtype=np.int32)
@@ -219,6 +228,11 @@ class State:
             lib().orc_state_destroy(C.c_void_p(self.h))
             self.h = None
 
+    def clone(self):
+        s = State.__new__(State)
+        s.h = lib().orc_state_clone(C.c_void_p(self.h))
+        return s
+
     def shape(self, name):
         dims = np.zeros(5, dtype=np.int32)
         nd = C.c_int(0)
@@ -238,8 +252,9 @@ class State:
 
     def __setitem__(self, name, value):
         e = REGISTRY[VAR_ID[name]]
-        a = np.asfortranarray(np.asarray(value, dtype=_NP[e["dtype"]]))
+        a = np.asarray(value, dtype=_NP[e["dtype"]])
         if a.ndim:
+            a = np.asfortranarray(a)
             assert a.shape == self.shape(name), (name, a.shape, self.shape(name))
         rc = lib().orc_set(C.c_void_p(self.h), e["id"], _ptr(a), a.nbytes)
         assert rc == 0, (name, rc)

@@ -71,6 +71,10 @@ def lib():
         L.spdy_batch_fourier_inv.argtypes = [vp, vp, ci, ci]
         L.spdy_batch_fourier_dir.argtypes = [vp, vp, ci]
         L.spdy_bench_roundtrip.argtypes = [vp, vp, ci, ci, vp, vp]
+        L.spdy_clone_state.argtypes = [i64, vp, ci]
+        L.spdy_perturb_temperature.argtypes = [vp, ci, C.c_ulonglong, C.c_double]
+        L.spdy_batch_spectral2grid.argtypes = [vp, ci]
+        L.spdy_profile_step.argtypes = [vp, vp, ci, vp, vp]
         L.spdy_debug_physics.argtypes = [i64] + [vp] * 11
         L.spdy_debug_raw_step.argtypes = [i64, ci, ci, ci]
         L.spdy_debug_get_corh.argtypes = [i64, vp, vp]
@@ -149,6 +153,47 @@ class _SpeedyDriver:
         lib().spdy_run_steps(_ptr(s), _ptr(c), s.shape[0], int(nsteps), _ptr(err))
         return err
 
+    # ---- ensemble extensions (no reference counterpart)
+    @staticmethod
+    def clone_state(src_state, dst_states):
+        d = np.ascontiguousarray(dst_states, dtype=np.int64)
+        return int(lib().spdy_clone_state(int(src_state), _ptr(d), d.shape[0]))
+
+    @staticmethod
+    def perturb_temperature(states, seed, sigma):
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        return int(lib().spdy_perturb_temperature(_ptr(s), s.shape[0], int(seed), float(sigma)))
+
+    @staticmethod
+    def batch_spectral2grid(states):
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        return int(lib().spdy_batch_spectral2grid(_ptr(s), s.shape[0]))
+
+    @staticmethod
+    def ensemble_sums(states, var_name, shift=None):
+        """Per-element sum and sum of squared deviations from ``shift`` over the listed members (device reduction)."""
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        e = REGISTRY[VAR_ID[var_name]]
+        n = int(np.prod(e["shape"])) * (2 if e["dtype"] == "c16" else 1)
+        out1, out2 = np.zeros(n), np.zeros(n)
+        sh = None if shift is None else np.ascontiguousarray(np.asarray(shift, dtype=np.float64).ravel(order="F"))
+        rc = lib().spdy_ensemble_sums(_ptr(s), s.shape[0], e["id"], None if sh is None else _ptr(sh), _ptr(out1), _ptr(out2))
+        if rc != 0:
+            raise RuntimeError(f"spdy_ensemble_sums({var_name}) failed: {rc}")
+        shp = tuple(e["shape"])
+        return out1.reshape(shp, order="F"), out2.reshape(shp, order="F")
+
+    @staticmethod
+    def profile_step(state_containers, control_containers):
+        s = np.ascontiguousarray(state_containers, dtype=np.int64)
+        c = np.ascontiguousarray(control_containers, dtype=np.int64)
+        ms = np.zeros(10, dtype=np.float32)
+        err = np.zeros(s.shape[0], dtype=np.int32)
+        lib().spdy_profile_step(_ptr(s), _ptr(c), s.shape[0], _ptr(ms), _ptr(err))
+        names = ["forcing", "pre_ops", "legendre_inv", "fft_inv", "grid_dyn", "physics", "fft_fwd", "legendre_dir",
+                 "spec_step", "post"]
+        return dict(zip(names, (float(x) for x in ms))), err
+
     @staticmethod
     def check(state):
         return int(lib().spdy_check(int(state)))
@@ -188,7 +233,9 @@ def _make_accessors(entry):
         return out
 
     def setter(state, value, n_months=None):
-        a = np.asfortranarray(np.asarray(value, dtype=dt))
+        a = np.asarray(value, dtype=dt)
+        if a.ndim:
+            a = np.asfortranarray(a)
         rc = lib().spdy_set(int(state), vid, _ptr(a), a.nbytes)
         if rc != 0:
             raise RuntimeError(f"spdy_set({entry['name']}) failed with code {rc} (shape {a.shape})")

@@ -169,6 +169,117 @@ int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, 
     return 0;
 }
 
+// ---- ensemble set-up / output extensions ----------------------------------------------------------------------
+namespace spdy {
+__global__ void __launch_bounds__(256) k_clone_lane(double *arena, long long tile_elems, int st, int sl, int dt, int dl, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) arena[((long long)dt * tile_elems + i) * TILE + dl] = arena[((long long)st * tile_elems + i) * TILE + sl];
+}
+// counter-based generator (splitmix64) + Box-Muller: N(0, sigma) per (member, grid point, level)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(128) k_noise_grid(const Ctx c, long long dst, unsigned long long seed, double sigma, int nlev) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    const unsigned long long member = (unsigned long long)c.tiles[t] * TILE + lane;
+    for (int k = 0; k < nlev; k++) {
+        const unsigned long long ctr = (member * KX + k) * NG + q;
+        const unsigned long long a = mix64(seed ^ (ctr * 2)), b = mix64(seed ^ (ctr * 2 + 1));
+        const double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0), u2 = (b >> 11) * (1.0 / 9007199254740992.0);
+        *(scp(c, t, dst + (long long)k * NG, lane) + (size_t)q * TILE) = sigma * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+}
+__global__ void __launch_bounds__(256) k_add_spec(const Ctx c, FieldRef src, long long dst_off, int n) {
+    const int lane = threadIdx.x & 31, t = blockIdx.y;
+    if (!lane_active(c, t, lane)) return;
+    const double *s = refp(c, t, src, lane);
+    double *d = stp(c, t, dst_off, lane);
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) d[(size_t)i * TILE] += s[(size_t)i * TILE];
+}
+}  // namespace spdy
+
+extern "C" {
+// copy the complete device state of `src` into every member of `dst` (ensemble set-up from one initialised member)
+int spdy_clone_state(int64_t src, const int64_t *dst, int n) {
+    Member *ms = member_of(src);
+    if (!ms) return -1;
+    for (int i = 0; i < n; i++) {
+        Member *md = member_of(dst[i]);
+        if (!md || md == ms) continue;
+        k_clone_lane<<<(int)((E.st_elems + 255) / 256), 256, 0, E.stream>>>(E.st, E.st_elems, ms->tile, ms->lane, md->tile, md->lane, E.st_elems);
+        if (ms->n_months >= 0) {
+            ensure_sst_months(ms->n_months + 2);
+            k_clone_lane<<<(int)((E.sst_elems + 255) / 256), 256, 0, E.stream>>>(E.sst, E.sst_elems, ms->tile, ms->lane, md->tile, md->lane, E.sst_elems);
+        }
+        COUNT(2);
+        md->initialized = ms->initialized, md->n_months = ms->n_months, md->current_step = ms->current_step;
+        md->bound_ctl = -1;
+        memcpy(md->lon, ms->lon, sizeof(ms->lon)), memcpy(md->lat, ms->lat, sizeof(ms->lat)), memcpy(md->lev, ms->lev, sizeof(ms->lev));
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    return 0;
+}
+// t_grid += N(0, sigma) i.i.d. per grid point, then t = grid2spec(t_grid) on time level 1 -- the perturbed-IC ensemble of
+// examples/Ensemble_forecast.ipynb cell 8, done for all listed members on the device (linear: t += grid2spec(noise))
+int spdy_perturb_temperature(const int64_t *hs, int n, unsigned long long seed, double sigma) {
+    engine_init();
+    const ScratchLayout &L = E.L;
+    const int nt = prepare_members(hs, n);
+    std::vector<FieldRef> src, dst;
+    for (int k = 0; k < KX; k++) src.push_back(REF_SCR | (L.tg + (long long)k * NG)), dst.push_back(REF_SCR | (L.sfwd + (long long)k * NSP));
+    for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
+        const int ntc = std::min(E.chunk_tiles, nt - t0);
+        Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);
+        k_noise_grid<<<dim3(NG / 4, ntc), 128, 0, E.stream>>>(c, L.tg, seed, sigma, KX);
+        run_forward_plain(c, src, dst);
+        k_add_spec<<<dim3(256, ntc), 256, 0, E.stream>>>(c, REF_SCR | L.sfwd, E.off[V_t], NSP * KX);
+        COUNT(2);
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    return 0;
+}
+// transform_spectral2grid for a list of members in one go (chunked)
+int spdy_batch_spectral2grid(const int64_t *hs, int n) {
+    engine_init();
+    const int nt = prepare_members(hs, n);
+    for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
+        Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, std::min(E.chunk_tiles, nt - t0));
+        s2g_ctx(c);
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    return 0;
+}
+// one model step of the listed members with device events between kernel classes; ms[10] per class (summed over chunks):
+// forcing, pre-ops, legendre_inv, fft_inv, grid_dyn, physics, fft_fwd, legendre_dir, spec_step, post
+int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, int *err) {
+    engine_init();
+    if (!P.made) {
+        for (int i = 0; i < 64; i++) CK(cudaEventCreate(&P.ev[i]));
+        P.made = true;
+    }
+    const int saved = E.chunk_tiles;
+    for (int i = 0; i < PC_COUNT; i++) ms[i] = 0.f;
+    // profile chunk by chunk: step_members with one chunk at a time would change semantics, so mark inside the loop
+    P.on = true, P.n = 0;
+    // limit event usage: only the first chunk of the step is instrumented (events are reused per class otherwise)
+    E.chunk_tiles = saved;
+    step_members(hs, cs, n, 1, err, true);
+    P.on = false;
+    int start = -1;
+    for (int i = 0; i < P.n; i++) {
+        if (P.cls[i] < 0) { start = i; continue; }
+        if (start < 0 || i == 0) continue;
+        float t;
+        CK(cudaEventElapsedTime(&t, P.ev[i - 1], P.ev[i]));
+        ms[P.cls[i]] += t;
+    }
+    return P.n;
+}
+}  // extern "C"
+
 static double *g_sums = nullptr;
 static size_t g_sums_n = 0;
 int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **out, size_t *nelem) {

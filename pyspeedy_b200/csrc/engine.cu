@@ -30,6 +30,24 @@ static inline void ck(cudaError_t e, const char *file, int line, const char *wha
 static long long g_launches = 0;
 #define COUNT(n) (g_launches += (n))
 
+// optional per-kernel-class device timing (spdy_profile_step): events between the stages of one step
+enum ProfClass { PC_FORCING = 0, PC_PREOPS, PC_LEG_INV, PC_FFT_INV, PC_GRID_DYN, PC_PHYSICS, PC_FFT_FWD, PC_LEG_DIR,
+                 PC_SPEC_STEP, PC_POST, PC_COUNT };
+struct Profiler {
+    bool on = false;
+    cudaEvent_t ev[64];
+    int cls[64];
+    int n = 0;
+    bool made = false;
+};
+static Profiler P;
+static void prof_mark(cudaStream_t s, int cls) {  // marks the END of a stage of class `cls` (cls < 0: start)
+    if (!P.on || P.n >= 64) return;
+    cudaEventRecord(P.ev[P.n], s);
+    P.cls[P.n] = cls;
+    P.n++;
+}
+
 // ---------------------------------------------------------------------------------------------- layouts
 ScratchLayout make_scratch_layout() {
     ScratchLayout L;
@@ -408,13 +426,17 @@ __global__ void __launch_bounds__(256) k_ens_sums(const Ctx c, long long off, lo
 // ---------------------------------------------------------------------------------------- kernel schedules
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     launch_legendre_inv(E.stream, c, d, n, E.L.four);
+    prof_mark(E.stream, PC_LEG_INV);
     launch_fft_inv(E.stream, c, d, n, E.L.four);
+    prof_mark(E.stream, PC_FFT_INV);
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
     for (int m = 0; m < FM_NMODES; m++)
         if (counts[m]) launch_fft_fwd(E.stream, c, m, lists[m], counts[m], E.L.four), COUNT(1);
+    prof_mark(E.stream, PC_FFT_FWD);
     launch_legendre_dir(E.stream, c, outs, nout, E.L.four);
+    prof_mark(E.stream, PC_LEG_DIR);
     COUNT(1);
 }
 // forward transform of `n` plain grid fields given as refs -> spectral refs
@@ -470,25 +492,32 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     launch_uvspec(E.stream, c, E.off[V_vor] + 7ll * NSP, E.off[V_div] + 7ll * NSP, REF_SCR | L.ucosp8, REF_SCR | L.vcosp8, 1);
     launch_gradient(E.stream, c, E.off[V_ps] + (long long)(j2 - 1) * NSP, REF_SCR | L.dpx, REF_SCR | L.dpy);
     COUNT(4);
+    prof_mark(E.stream, PC_PREOPS);
     run_inverse(c, E.d_inv[j2 - 1], 77);
     launch_grid_dyn(E.stream, c, L);
+    prof_mark(E.stream, PC_GRID_DYN);
     launch_physics(E.stream, c, L, nullptr);
+    prof_mark(E.stream, PC_PHYSICS);
     COUNT(2);
     run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT);
     launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx);
+    prof_mark(E.stream, PC_SPEC_STEP);
     COUNT(1);
 }
 
 // do_single_step (speedy.f90:20-74) for one chunk of tiles
 static void run_model_step(const Ctx &c, bool any_daily) {
+    prof_mark(E.stream, -1);
     launch_control_pre(E.stream, c);
     COUNT(1);
     if (any_daily) run_forcing(c, 1);
+    prof_mark(E.stream, PC_FORCING);
     run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2);
     launch_step_increment(E.stream, c);
     launch_diag(E.stream, c, 2, 0);
     launch_control_post(E.stream, c);
     launch_couple(E.stream, c, 0);
+    prof_mark(E.stream, PC_POST);
     COUNT(4);
 }
 
@@ -655,9 +684,13 @@ static int init_member(Member &m, Control &ctl) {
     return 0;
 }
 
+static void s2g_ctx(const Ctx &c);
 static void s2g_member(Member &m) {  // prognostics.f90:125-154
-    const ScratchLayout &L = E.L;
     Ctx c = single_ctx(m);
+    s2g_ctx(c);
+}
+static void s2g_ctx(const Ctx &c) {
+    const ScratchLayout &L = E.L;
     launch_uvspec(E.stream, c, E.off[V_vor], E.off[V_div], REF_SCR | L.ucos, REF_SCR | L.vcos, KX);
     COUNT(1);
     std::vector<InvDesc> v;
@@ -670,7 +703,7 @@ static void s2g_member(Member &m) {  // prognostics.f90:125-154
     }
     v.push_back(InvDesc{E.off[V_ps], L.pslg, 1, 0});
     run_inverse_list(c, v);
-    k_s2g_finish<<<dim3(NG / 4, 1), 128, 0, E.stream>>>(c, L);
+    k_s2g_finish<<<dim3(NG / 4, c.ntiles), 128, 0, E.stream>>>(c, L);
     COUNT(1);
     CK(cudaStreamSynchronize(E.stream));
 }

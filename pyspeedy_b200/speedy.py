@@ -304,6 +304,41 @@ class SpeedyEns:
     def to_dataframe(self, variables=None):
         return Dataset.merge([member.to_dataframe(variables=variables) for member in self])
 
+    # ---- ensemble extensions (no reference counterpart) -----------------------------------------------------
+    def handles(self):
+        s = np.array([m._state_cnt for m in self], dtype=np.int64)  # noqa
+        c = np.array([m._control_cnt for m in self], dtype=np.int64)  # noqa
+        return s, c
+
+    def set_bc(self, bc_file=None, sst_anomaly=None, perturb_sigma=None, seed=1234):
+        """Initialise every member with the same boundary conditions: member 0 runs the full ``Speedy.set_bc`` and
+        its device state is cloned into the others (identical to calling ``set_bc`` per member, which is how the
+        reference does it, but one initialisation instead of N).  ``perturb_sigma`` adds the i.i.d. N(0, sigma)
+        grid-point temperature perturbation of examples/Ensemble_forecast.ipynb to every member."""
+        self.members[0].set_bc(bc_file=bc_file, sst_anomaly=sst_anomaly)
+        s, _ = self.handles()
+        _speedy.clone_state(int(s[0]), s[1:])
+        for m in self.members[1:]:
+            m._initialized_bc = m._initialized_ssta = True
+        if perturb_sigma:
+            _speedy.perturb_temperature(s, seed, perturb_sigma)
+
+    def mean_and_spread(self, variables=None):
+        """Ensemble mean and spread (std, ddof=0) of grid variables; the sums are reduced on the device."""
+        if variables is None:
+            variables = DEFAULT_OUTPUT_VARS
+        s, _ = self.handles()
+        _speedy.batch_spectral2grid(s)
+        out = {}
+        for v in variables:
+            shift = self.members[0][v]
+            s1, s2 = _speedy.ensemble_sums(s, v, shift=shift)
+            n = float(self.n_members)
+            mean = s1 / n
+            var = np.maximum(s2 / n - (mean - shift) ** 2, 0.0)
+            out[v] = (mean, np.sqrt(var))
+        return out
+
     def run(self, callbacks=None, steps_per_call=1):
         """Run every member between the start and end dates (pyspeedy/speedy.py:547-593).
 
