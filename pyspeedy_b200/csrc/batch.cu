@@ -280,6 +280,12 @@ int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, in
 }
 }  // extern "C"
 
+extern "C" {
+// bracket a region for `ncu --profile-from-start off`
+int spdy_profiler_start(void) { return (int)cudaProfilerStart(); }
+int spdy_profiler_stop(void) { return (int)cudaProfilerStop(); }
+}
+
 static double *g_sums = nullptr;
 static size_t g_sums_n = 0;
 int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **out, size_t *nelem) {

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(128) k_grid_dyn(const Ctx c, const ScratchLayo
 }
 
 // -------------------------------------------------------------------------- spectral tendencies + time step
+// Complex helpers (used by the grid<->spectral service kernels)
 struct C2 {
     double r, i;
 };
@@ -88,7 +89,7 @@ __device__ __forceinline__ C2 operator*(double s, C2 a) { return {s * a.r, s * a
 __device__ __forceinline__ C2 operator*(C2 a, double s) { return {a.r * s, a.i * s}; }
 __device__ __forceinline__ C2 operator-(C2 a) { return {-a.r, -a.i}; }
 
-// (vor, div) of vel2vort at coefficient (m,n) from spectral u, v (spectral.f90:160-186)
+// (vor, div) of vel2vort at coefficient (m,n) from spectral u, v (spectral.f90:160-186), complex form
 __device__ __forceinline__ void vdspec_elem(const GlobTables *G, const double *su, const double *sv, int m, int n,
                                             C2 &vor, C2 &dv) {
     const int q = m + MX * n;
@@ -111,70 +112,116 @@ __device__ __forceinline__ void vdspec_elem(const GlobTables *G, const double *s
     }
 }
 
-// leapfrog + Robert-Asselin-Williams filter on one coefficient (time_stepping.f90:164-188)
-__device__ __forceinline__ void raw_update(double *p1, double *p2, C2 fdt, double trf, int j1, double dt, double eps,
-                                           bool act) {
-    fdt = fdt * trf;  // truncate (ix == 4*iy)
-    C2 o1 = ld2(p1), o2 = ld2(p2);
-    const C2 fnew = o1 + dt * fdt;
-    C2 oj1 = (j1 == 1) ? o1 : o2;
-    o1 = oj1 + (D_WIL * eps) * ((o1 - 2.0 * oj1) + fnew);
-    if (j1 == 1) oj1 = o1;  // output(:,:,j1) aliases the updated level 1
-    o2 = fnew - ((1.0 - D_WIL) * eps) * ((o1 - 2.0 * oj1) + fnew);
-    if (act) {
-        st2(p1, o1);
-        st2(p2, o2);
+// Same operator for ONE component (cc = 0 real, 1 imaginary).  su/sv point at the (m,n) element of this component;
+// the i*gradx term needs the other component of the centre element only: `oth` = +TILE (cc = 0) or -TILE (cc = 1).
+// WANT: 1 = vorticity only, 2 = divergence only, 3 = both.
+template <int WANT>
+__device__ __forceinline__ void vdspec_comp(const double gx, const double ym, const double yp, const double *su,
+                                            const double *sv, const int n, const int cc, double &vor, double &dv) {
+    const long long up = (long long)M2 * TILE, oth = cc ? -TILE : TILE;
+    // (a+bi)*i = -b + ai : real part uses -imag, imaginary part uses +real
+    if (WANT & 1) {
+        const double zc = cc ? gx * sv[oth] : -(gx * sv[oth]);
+        if (n == 0) vor = zc - yp * su[up];
+        else if (n == NX - 1) vor = ym * su[-up];
+        else vor = (ym * su[-up] - yp * su[up]) + zc;
+    }
+    if (WANT & 2) {
+        const double zp = cc ? gx * su[oth] : -(gx * su[oth]);
+        if (n == 0) dv = zp + yp * sv[up];
+        else if (n == NX - 1) dv = (-ym) * sv[-up];
+        else dv = ((-ym) * sv[-up] + yp * sv[up]) + zp;
     }
 }
 
-__global__ void __launch_bounds__(128) k_spec_step(const Ctx c, const ScratchLayout L, const int j1, const double dt,
-                                                   const double eps, const int impl_idx) {
-    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+// leapfrog + Robert-Asselin-Williams filter on one component (time_stepping.f90:164-188)
+__device__ __forceinline__ void raw_update(double *p1, double *p2, double fdt, const double trf, const int j1,
+                                           const double dt, const double eps, const bool act) {
+    fdt = fdt * trf;  // truncate (ix == 4*iy)
+    double o1 = *p1, o2 = *p2;
+    const double fnew = o1 + dt * fdt;
+    double oj1 = (j1 == 1) ? o1 : o2;
+    o1 = oj1 + (D_WIL * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (j1 == 1) oj1 = o1;  // output(:,:,j1) aliases the updated level 1
+    o2 = fnew - ((1.0 - D_WIL) * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (act) *p1 = o1, *p2 = o2;
+}
+
+// Vorticity and tracer: no vertical coupling -> one thread per (coefficient, component, level)
+// (tendencies.f90:238-268 spectral part, time_stepping.f90:78-144)
+__global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const ScratchLayout L, const int j1, const double dt,
+                                                      const double eps, const int impl_idx) {
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y;
+    // w = ((q * 2 + cc) * KX + k)
+    const int k = w % KX, cc = (w / KX) & 1, q = w / (2 * KX);
     if (q >= NSPC) return;
     const int m = q % MX, n = q / MX;
     const GlobTables *G = c.G;
     const ImplTables *I = &G->impl[impl_idx];
-    const size_t e = (size_t)(2 * m + M2 * n) * TILE, lev = (size_t)NSP * TILE;
+    const size_t e = (size_t)(2 * m + cc + M2 * n) * TILE, lev = (size_t)NSP * TILE, tl = (size_t)KX * lev;
     const bool act = lane_active(c, t, lane);
-    const double *F = scp(c, t, L.sfwd, lane) + e;  // forward-transform outputs, slot s at F + s*lev
-    // state, time level 1 (0-based 0) and 2
-    double *vor = stp(c, t, c.off[V_vor], lane) + e, *dvs = stp(c, t, c.off[V_div], lane) + e,
-           *tt = stp(c, t, c.off[V_t], lane) + e, *trs = stp(c, t, c.off[V_tr], lane) + e,
+    const double *F = scp(c, t, L.sfwd, lane) + e;
+    double *vor = stp(c, t, c.off[V_vor], lane) + e + k * lev, *trs = stp(c, t, c.off[V_tr], lane) + e + k * lev;
+    const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q], trf = G->trfilt[q];
+    double vo, dq, dum;
+    vdspec_comp<1>(gx, ym, yp, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, n, cc, vo, dum);
+    vdspec_comp<2>(gx, ym, yp, F + (FW_UQ + k) * lev, F + (FW_VQ + k) * lev, n, cc, dum, dq);
+    double trdt = dq + F[(FW_QT + k) * lev];
+    const double v1 = *vor, q1 = *trs;
+    const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
+    double vordt = (vo - dmp * v1) * I->dmp1[q];
+    if (k == 0 && m == 0) vordt = vordt - (1.0 / ((double)(24.0f * 30.0f) * FL(3600.0))) * v1;
+    vordt = (vordt - dmps * v1) * I->dmp1s[q];
+    const double ctq = q1 + *(stp(c, t, c.off_qcorh, lane) + e) * c_T.qcorv[k];
+    trdt = (trdt - dmpd * ctq) * I->dmp1d[q];
+    raw_update(vor, vor + tl, vordt, trf, j1, dt, eps, act);
+    raw_update(trs, trs + tl, trdt, trf, j1, dt, eps, act);
+}
+
+// Divergence, temperature, log(ps): coupled in the vertical by the semi-implicit scheme -> one thread per
+// (coefficient, component) holding the 8-level columns (tendencies.f90:283-352, implicit.f90:234-289)
+__global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const ScratchLayout L, const int j1, const double dt,
+                                                      const double eps, const int impl_idx) {
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    const int cc = w & 1, q = w >> 1;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const GlobTables *G = c.G;
+    const ImplTables *I = &G->impl[impl_idx];
+    const size_t e = (size_t)(2 * m + cc + M2 * n) * TILE, lev = (size_t)NSP * TILE, tl = (size_t)KX * lev;
+    const bool act = lane_active(c, t, lane);
+    const double *F = scp(c, t, L.sfwd, lane) + e;
+    double *dvs = stp(c, t, c.off[V_div], lane) + e, *tt = stp(c, t, c.off[V_t], lane) + e,
            *ps = stp(c, t, c.off[V_ps], lane) + e;
     const double *phi = stp(c, t, c.off[V_phi], lane) + e;
-    const size_t tl = (size_t)KX * lev;  // time-level stride of (mx,nx,kx,2) arrays
     const double el2 = G->el2[q], trf = G->trfilt[q];
+    const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q];
 
-    C2 divdt[KX], tdt[KX];
-    // ---- A. grid-point tendencies converted to spectral space (tendencies.f90:238-268)
-    // vorticity tendency is final after diffusion: handle it level by level at the end (needs no vertical coupling)
+    double divdt[KX], tdt[KX], d1[KX];
+    // ---- A. grid-point tendencies in spectral space (tendencies.f90:238-268)
 #pragma unroll
     for (int k = 0; k < KX; k++) {
-        C2 vo, dv;
-        vdspec_elem(G, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, m, n, vo, dv);
-        const C2 ke = ld2(F + (FW_KE + k) * lev);
-        divdt[k] = dv - ((-ke) * el2);
-        C2 dum, dT;
-        vdspec_elem(G, F + (FW_UT + k) * lev, F + (FW_VT + k) * lev, m, n, dum, dT);
-        tdt[k] = dT + ld2(F + (FW_TT + k) * lev);
+        double dv, dT, dum;
+        vdspec_comp<2>(gx, ym, yp, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, n, cc, dum, dv);
+        divdt[k] = dv - ((-F[(FW_KE + k) * lev]) * el2);
+        vdspec_comp<2>(gx, ym, yp, F + (FW_UT + k) * lev, F + (FW_VT + k) * lev, n, cc, dum, dT);
+        tdt[k] = dT + F[(FW_TT + k) * lev];
+        d1[k] = dvs[k * lev];
     }
-    C2 psdt = ld2(F + FW_PS * lev);
-    if (q == 0) psdt = {0.0, 0.0};
-    // ---- B. spectral tendencies with time level 1 (tendencies.f90:283-352, alph = 0.5 branch of :31-38)
-    C2 d1[KX];
-#pragma unroll
-    for (int k = 0; k < KX; k++) d1[k] = ld2(dvs + k * lev);
-    C2 dmeanc = {0.0, 0.0};
+    double psdt = F[FW_PS * lev];
+    if (q == 0) psdt = 0.0;
+    // ---- B. spectral tendencies with time level 1 (tendencies.f90:283-352)
+    double dmeanc = 0.0;
 #pragma unroll
     for (int k = 0; k < KX; k++) dmeanc = dmeanc + d1[k] * c_T.dhs[k];
     psdt = psdt - dmeanc;
-    if (q == 0) psdt = {0.0, 0.0};
+    if (q == 0) psdt = 0.0;
     {
-        C2 sig[KX + 1], dumk[KX + 1];
-        sig[0] = {0.0, 0.0}, sig[KX] = {0.0, 0.0};
+        double sig[KX + 1], dumk[KX + 1];
+        sig[0] = 0.0, sig[KX] = 0.0;
 #pragma unroll
         for (int k = 0; k < KX - 1; k++) sig[k + 1] = sig[k] - c_T.dhs[k] * (d1[k] - dmeanc);
-        dumk[0] = {0.0, 0.0}, dumk[KX] = {0.0, 0.0};
+        dumk[0] = 0.0, dumk[KX] = 0.0;
 #pragma unroll
         for (int k = 1; k < KX; k++) dumk[k] = sig[k] * (c_T.tref[k] - c_T.tref[k - 1]);
 #pragma unroll
@@ -182,19 +229,19 @@ __global__ void __launch_bounds__(128) k_spec_step(const Ctx c, const ScratchLay
             tdt[k] = ((tdt[k] - (dumk[k + 1] + dumk[k]) * c_T.dhsr[k]) + c_T.tref3[k] * (sig[k + 1] + sig[k])) -
                      c_T.tref2[k] * dmeanc;
     }
-    const C2 ps1 = ld2(ps);
+    const double ps1 = *ps;
 #pragma unroll
     for (int k = 0; k < KX; k++) {
-        const C2 g = ld2(phi + k * lev) + (D_RGAS * c_T.tref[k]) * ps1;
+        const double g = phi[k * lev] + (D_RGAS * c_T.tref[k]) * ps1;
         divdt[k] = divdt[k] - ((-g) * el2);
     }
     // ---- C. semi-implicit correction (implicit.f90:234-289)
     {
-        C2 yf[KX];
+        double yf[KX];
         const double elz = I->elz[q];
 #pragma unroll
         for (int k = 0; k < KX; k++) {
-            C2 ye = {0.0, 0.0};
+            double ye = 0.0;
 #pragma unroll
             for (int k1 = 0; k1 < KX; k1++) ye = ye + I->xd[k + KX * k1] * tdt[k1];
             ye = ye + (D_RGAS * c_T.tref[k]) * psdt;
@@ -202,7 +249,7 @@ __global__ void __launch_bounds__(128) k_spec_step(const Ctx c, const ScratchLay
         }
         const int l = m + n;
 #pragma unroll
-        for (int k = 0; k < KX; k++) divdt[k] = {0.0, 0.0};
+        for (int k = 0; k < KX; k++) divdt[k] = 0.0;
         if (l != 0) {
             const double *xj = I->xj + (size_t)KX * KX * (l - 1);
 #pragma unroll
@@ -221,57 +268,58 @@ __global__ void __launch_bounds__(128) k_spec_step(const Ctx c, const ScratchLay
     const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
     const double dmp1 = I->dmp1[q], dmp1d = I->dmp1d[q], dmp1s = I->dmp1s[q];
     const double sdrag = 1.0 / ((double)(24.0f * 30.0f) * FL(3600.0));
-    const C2 tcorh = ld2(stp(c, t, c.off_tcorh, lane) + e), qcorh = ld2(stp(c, t, c.off_qcorh, lane) + e);
+    const double tcorh = *(stp(c, t, c.off_tcorh, lane) + e);
     raw_update(ps, ps + lev, psdt, trf, j1, dt, eps, act);
 #pragma unroll
     for (int k = 0; k < KX; k++) {
-        const C2 v1 = ld2(vor + k * lev), t1 = ld2(tt + k * lev), q1 = ld2(trs + k * lev);
-        // vorticity tendency (spectral.f90:160-186 on utend, vtend)
-        C2 vo, dvx;
-        vdspec_elem(G, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, m, n, vo, dvx);
-        C2 dq, dumq;
-        vdspec_elem(G, F + (FW_UQ + k) * lev, F + (FW_VQ + k) * lev, m, n, dumq, dq);
-        C2 trdt = dq + ld2(F + (FW_QT + k) * lev);
-        C2 vordt = (vo - dmp * v1) * dmp1;
-        C2 dd = (divdt[k] - dmpd * d1[k]) * dmp1d;
-        const C2 ctmp = t1 + tcorh * c_T.tcorv[k];
-        C2 td = (tdt[k] - dmp * ctmp) * dmp1;
-        if (k == 0 && m == 0) {
-            vordt = vordt - sdrag * v1;
-            dd = dd - sdrag * d1[k];
-        }
-        vordt = (vordt - dmps * v1) * dmp1s;
+        const double t1 = tt[k * lev];
+        double dd = (divdt[k] - dmpd * d1[k]) * dmp1d;
+        const double ctmp = t1 + tcorh * c_T.tcorv[k];
+        double td = (tdt[k] - dmp * ctmp) * dmp1;
+        if (k == 0 && m == 0) dd = dd - sdrag * d1[k];
         dd = (dd - dmps * d1[k]) * dmp1s;
         td = (td - dmps * ctmp) * dmp1s;
-        const C2 ctq = q1 + qcorh * c_T.qcorv[k];
-        trdt = (trdt - dmpd * ctq) * dmp1d;
-        raw_update(vor + k * lev, vor + tl + k * lev, vordt, trf, j1, dt, eps, act);
         raw_update(dvs + k * lev, dvs + tl + k * lev, dd, trf, j1, dt, eps, act);
         raw_update(tt + k * lev, tt + tl + k * lev, td, trf, j1, dt, eps, act);
-        raw_update(trs + k * lev, trs + tl + k * lev, trdt, trf, j1, dt, eps, act);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ diagnostics
-// diagnostics.f90:16-74.  One warp per (tile, level); sums in the reference's order (m outer, n inner).
-__global__ void __launch_bounds__(32) k_diag(const Ctx c, const int time_lev) {
-    const int lane = threadIdx.x, k = blockIdx.x, t = blockIdx.y;
+// diagnostics.f90:16-74 in two deterministic stages: (1) one warp per (level, m) sums over n; (2) one warp per tile
+// adds the 30 partial sums in m order and applies the range check.
+__global__ void __launch_bounds__(32) k_diag_partial(const Ctx c, const int time_lev, const long long part) {
+    const int lane = threadIdx.x, k = blockIdx.x / (MX - 1), m = 1 + blockIdx.x % (MX - 1), t = blockIdx.y;
     const size_t lev = (size_t)NSP * TILE, tl = (size_t)KX * lev * (time_lev - 1);
-    const double *vor = stp(c, t, c.off[V_vor], lane) + tl + k * lev, *dv = stp(c, t, c.off[V_div], lane) + tl + k * lev,
-                 *tt = stp(c, t, c.off[V_t], lane) + tl + k * lev;
+    const double *vor = stp(c, t, c.off[V_vor], lane) + tl + k * lev, *dv = stp(c, t, c.off[V_div], lane) + tl + k * lev;
     const GlobTables *G = c.G;
     double d1 = 0.0, d2 = 0.0;
-    for (int m = 1; m < MX; m++)
-        for (int n = 0; n < NX; n++) {
-            const size_t e = (size_t)(2 * m + M2 * n) * TILE;
-            const double em = G->elm2[m + MX * n];
-            const double vr = vor[e], vi = vor[e + TILE], dr = dv[e], di = dv[e + TILE];
-            const double ar = (-vr) * em, ai = (-vi) * em, br = (-dr) * em, bi = (-di) * em;
-            d1 = d1 - (ar * vr - ai * (-vi));
-            d2 = d2 - (br * dr - bi * (-di));
+#pragma unroll 8
+    for (int n = 0; n < NX; n++) {
+        const size_t e = (size_t)(2 * m + M2 * n) * TILE;
+        const double em = G->elm2[m + MX * n];
+        const double vr = vor[e], vi = vor[e + TILE], dr = dv[e], di = dv[e + TILE];
+        const double ar = (-vr) * em, ai = (-vi) * em, br = (-dr) * em, bi = (-di) * em;
+        d1 = d1 - (ar * vr - ai * (-vi));
+        d2 = d2 - (br * dr - bi * (-di));
+    }
+    double *p = scp(c, t, part + 2 * (k * (MX - 1) + (m - 1)), lane);
+    p[0] = d1, p[TILE] = d2;
+}
+__global__ void __launch_bounds__(32) k_diag_final(const Ctx c, const int time_lev, const long long part) {
+    const int lane = threadIdx.x, t = blockIdx.x;
+    const size_t lev = (size_t)NSP * TILE, tl = (size_t)KX * lev * (time_lev - 1);
+    const double *tt = stp(c, t, c.off[V_t], lane) + tl;
+    bool bad = false;
+    for (int k = 0; k < KX; k++) {
+        double d1 = 0.0, d2 = 0.0;
+        for (int m = 0; m < MX - 1; m++) {
+            const double *p = scp(c, t, part + 2 * (k * (MX - 1) + m), lane);
+            d1 += p[0], d2 += p[TILE];
         }
-    const double d3 = 0x1.6a09e6p-1 * tt[0];  // sqrt(0.5) REAL(4)
-    if (d1 > 500.0 || d2 > 500.0 || d3 < 180.0 || d3 > 320.0) slot(c, t, lane, SL_ERR) = -2.0;
+        const double d3 = 0x1.6a09e6p-1 * tt[k * lev];  // sqrt(0.5) REAL(4)
+        bad = bad || (d1 > 500.0 || d2 > 500.0 || d3 < 180.0 || d3 > 320.0);
+    }
+    if (bad && lane_active(c, t, lane)) slot(c, t, lane, SL_ERR) = -2.0;
 }
 
 // --------------------------------------------------------------------------------------------- member control
@@ -333,9 +381,13 @@ void launch_grid_dyn(cudaStream_t s, const Ctx &c, const ScratchLayout &L) {
     k_grid_dyn<<<dim3(NG / 4, c.ntiles), 128, 0, s>>>(c, L);
 }
 void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j1, double dt, double eps, int impl_idx) {
-    k_spec_step<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+    k_spec_step_vq<<<dim3(NSPC * 2 * KX / 8, c.ntiles), 256, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+    k_spec_step_dt<<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
 }
-void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, int) { k_diag<<<dim3(KX, c.ntiles), 32, 0, s>>>(c, time_lev); }
+void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part) {
+    k_diag_partial<<<dim3(KX * (MX - 1), c.ntiles), 32, 0, s>>>(c, time_lev, part);
+    k_diag_final<<<c.ntiles, 32, 0, s>>>(c, time_lev, part);
+}
 void launch_control_pre(cudaStream_t s, const Ctx &c) { k_control_pre<<<c.ntiles, 32, 0, s>>>(c); }
 void launch_control_post(cudaStream_t s, const Ctx &c) { k_control_post<<<c.ntiles, 32, 0, s>>>(c); }
 void launch_step_increment(cudaStream_t s, const Ctx &c) { k_step_increment<<<c.ntiles, 32, 0, s>>>(c); }

@@ -3,6 +3,7 @@
 // (registry/templates/speedy_driver.f90.j2) and the orchestration of speedy.f90:20-74, initialization.f90:13-91,
 // time_stepping.f90:13-27 and prognostics.f90:125-219.  There is no CPU fallback: every entry point that
 // computes needs a CUDA device and aborts loudly without one.
+#include <cuda_profiler_api.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -62,6 +63,7 @@ ScratchLayout make_scratch_layout() {
     L.ucosp8 = take(NSP), L.vcosp8 = take(NSP), L.dpx = take(NSP), L.dpy = take(NSP);
     L.sfwd = take((long long)NSP * 80);
     L.four = take((long long)NFOUR * 80);
+    L.diagp = take(2ll * KX * (MX - 1));
     L.total = o;
     return L;
 }
@@ -514,7 +516,7 @@ static void run_model_step(const Ctx &c, bool any_daily) {
     prof_mark(E.stream, PC_FORCING);
     run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2);
     launch_step_increment(E.stream, c);
-    launch_diag(E.stream, c, 2, 0);
+    launch_diag(E.stream, c, 2, E.L.diagp);
     launch_control_post(E.stream, c);
     launch_couple(E.stream, c, 0);
     prof_mark(E.stream, PC_POST);
@@ -663,7 +665,7 @@ static int init_member(Member &m, Control &ctl) {
     run_forward_plain(c, {REF_SCR | L.px}, {REF_SCR | L.dpy});
     launch_init_spec(E.stream, c, REF_SCR | L.dpx, REF_SCR | L.dpy);
     k_set_slot<<<1, 32, 0, E.stream>>>(c, SL_ERR, 0.0);
-    launch_diag(E.stream, c, 1, 0);
+    launch_diag(E.stream, c, 1, E.L.diagp);
     COUNT(3);
     const int err = (int)get_slot_host(m, SL_ERR);
     if (err != 0) return err;
@@ -911,7 +913,7 @@ int spdy_check(int64_t h) {
     if (!m) return -1;
     Ctx c = single_ctx(*m);
     k_set_slot<<<1, 32, 0, E.stream>>>(c, SL_ERR, 0.0);
-    launch_diag(E.stream, c, 1, 0);
+    launch_diag(E.stream, c, 1, E.L.diagp);
     COUNT(2);
     return (int)get_slot_host(*m, SL_ERR);
 }

@@ -66,8 +66,11 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         qsat[k] = qsat_of(ta[k], psa, c_T.fsg[k]);
         rh[k] = qa[k] / qsat[k];
     }
-    double tt[KX], qt[KX];  // physics tendencies of T and q accumulated in the reference's order
+    // T and q tendencies are accumulated in registers in the reference's order of additions and written once
     double *ottend = scp(c, t, L.ttend, lane) + e, *oqtend = scp(c, t, L.trtend, lane) + e;
+    double tsum[KX], qsum[KX];
+#pragma unroll
+    for (int k = 0; k < KX; k++) tsum[k] = ottend[k * lev], qsum[k] = oqtend[k * lev];
 
     // ---- deep convection (convection.f90:27-253)
     int itop = KX + 1;  // 1-based level index as in the reference, 9 = no convection
@@ -162,12 +165,12 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
                 }
         }
     }
-    // physics.f90:128-131 ; tt_cnv(1) stays 0
-    tt[0] = 0.0, qt[0] = 0.0;
+    // physics.f90:128-131,140-141 ; tt_cnv(1) stays 0
+    tsum[0] = tsum[0] + 0.0, qsum[0] = qsum[0] + 0.0;
 #pragma unroll
     for (int k = 1; k < KX; k++) {
-        tt[k] = dfse[k] * rps * c_T.grdscp[k];
-        qt[k] = dfqa[k] * rps * c_T.grdsig[k];
+        tsum[k] = tsum[k] + dfse[k] * rps * c_T.grdscp[k];
+        qsum[k] = qsum[k] + dfqa[k] * rps * c_T.grdsig[k];
     }
     const int icnv = KX - itop;
 
@@ -197,12 +200,9 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
 #pragma unroll
         for (int k = 1; k < KX; k++) precls = precls - (c_T.dhs[k] * prg) * dql[k];
         precls = precls * psa;
-        // physics.f90:140-141: ttend = ttend + tt_cnv + tt_lsc  (sum order preserved below via separate adds)
+        // physics.f90:140-141: ttend = ttend + tt_cnv + tt_lsc
 #pragma unroll
-        for (int k = 0; k < KX; k++) {
-            ottend[k * lev] = (ottend[k * lev] + tt[k]) + dtl[k];
-            oqtend[k * lev] = (oqtend[k * lev] + qt[k]) + dql[k];
-        }
+        for (int k = 0; k < KX; k++) tsum[k] = tsum[k] + dtl[k], qsum[k] = qsum[k] + dql[k];
     }
     if (act) {
         *ST2D(V_cbmf) = cbmf;
@@ -333,8 +333,78 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         strat[lev] = eps1 * psa;
     }
 
+    // ---- vertical diffusion and shallow convection (vertical_diffusion.f90:30-146): independent of the radiation,
+    //      evaluated here so that se/rh/qsat/phi die before the long-wave sweeps (register pressure)
+    double tv[KX], qv[KX];
+    {
+        const double trshc = FL(6.0), trvdi = FL(24.0), trvds = FL(6.0), redshc = FL(0.5), rhgrad = FL(0.5), segrad = FL(0.1);
+        const double cshc = c_T.dhs[7] / FL(3600.0);
+        const double cvdi = (c_T.sigh[7] - c_T.sigh[1]) / (double)(6.0f * 3600.0f);
+        const double fshcq = cshc / trshc, fshcse = cshc / (trshc * CP);
+        const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * CP);
+#pragma unroll
+        for (int k = 0; k < KX; k++) tv[k] = 0.0, qv[k] = 0.0;
+        const double rsig6 = 1.0 / c_T.dhs[6], rsig7 = 1.0 / c_T.dhs[7];
+        {
+            const double drh0 = rhgrad * (c_T.fsg[7] - c_T.fsg[6]);
+            const double fvdiq2 = fvdiq * c_T.sigh[7];
+            const double dmse = se[7] - se[6] + ALHC * (qa[7] - qsat[6]);
+            const double drh = rh[7] - rh[6];
+            double fcnv = 1.0;
+            if (dmse >= 0.0) {
+                if (icnv > 0) fcnv = redshc;
+                const double fluxse = fcnv * fshcse * dmse;
+                tv[6] = fluxse * rsig6;
+                tv[7] = -fluxse * rsig7;
+                if (drh >= 0.0) {
+                    const double fluxq = fcnv * fshcq * qsat[7] * drh;
+                    qv[6] = fluxq * rsig6;
+                    qv[7] = -fluxq * rsig7;
+                }
+            } else if (drh > drh0) {
+                const double fluxq = fvdiq2 * qsat[6] * drh;
+                qv[6] = fluxq * rsig6;
+                qv[7] = -fluxq * rsig7;
+            }
+        }
+#pragma unroll
+        for (int k = 3; k <= KX - 2; k++)  // 1-based k
+            if (c_T.sigh[k] > 0.5) {
+                const double drh0 = rhgrad * (c_T.fsg[k] - c_T.fsg[k - 1]);
+                const double fvdiq2 = fvdiq * c_T.sigh[k];
+                const double drh = rh[k] - rh[k - 1];
+                if (drh >= drh0) {
+                    const double fluxq = fvdiq2 * qsat[k - 1] * drh;
+                    qv[k - 1] = qv[k - 1] + fluxq * (1.0 / c_T.dhs[k - 1]);
+                    qv[k] = qv[k] - fluxq * (1.0 / c_T.dhs[k]);
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < KX - 1; k++) {
+            const double se0 = se[k + 1] + segrad * (phi[k] - phi[k + 1]);
+            if (se[k] < se0) {
+                const double fluxse = fvdise * (se0 - se[k]);
+                tv[k] = tv[k] + fluxse * (1.0 / c_T.dhs[k]);
+                const double r1 = 1.0 / (1.0 - c_T.sigh[k + 1]);
+#pragma unroll
+                for (int k1 = k + 1; k1 < KX; k1++) tv[k1] = tv[k1] - fluxse * r1;
+            }
+        }
+    }
+    // moisture tendency: final for levels 1..kx-1 (the lowest level still needs the evaporation)
+#pragma unroll
+    for (int k = 0; k < KX - 1; k++) oqtend[k * lev] = qsum[k] + qv[k];
+    const double ta6 = ta[6], ta7 = ta[7], qa7 = qa[7], phi7 = phi[7];
+
     // ---- downward long-wave (longwave_radiation.f90:16-121)
     double st4a1[KX], st4a2[KX], dfabs[KX], flux[4];
+    double tau[4][KX], trsw_s[KX];  // one batch of independent loads (written above on short-wave steps)
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++)
+#pragma unroll
+        for (int k = 0; k < KX; k++) tau[jb][k] = tau2[(k + KX * jb) * lev];
+#pragma unroll
+    for (int k = 0; k < KX; k++) trsw_s[k] = ttrsw[k * lev];
     {
 #pragma unroll
         for (int k = 0; k < KX - 1; k++) st4a1[k] = ta[k] + c_T.wvi[k][1] * (ta[k + 1] - ta[k]);
@@ -355,7 +425,7 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         for (int k = 0; k < KX; k++) dfabs[k] = 0.0;
 #pragma unroll
         for (int jb = 0; jb < 2; jb++) {
-            const double emis = 1.0 - tau2[(0 + KX * jb) * lev];
+            const double emis = 1.0 - tau[jb][0];
             const double brad = fband_at(fb, ta[0], jb) * (st4a1[0] + emis * st4a2[0]);
             flux[jb] = emis * brad;
             dfabs[0] = dfabs[0] - flux[jb];
@@ -365,7 +435,7 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         for (int jb = 0; jb < 4; jb++)
 #pragma unroll
             for (int k = 1; k < KX; k++) {
-                const double tk = tau2[(k + KX * jb) * lev];
+                const double tk = tau[jb][k];
                 const double emis = 1.0 - tk;
                 const double brad = fband_at(fb, ta[k], jb) * (st4a1[k] + emis * st4a2[k]);
                 dfabs[k] = dfabs[k] + flux[jb];
@@ -392,16 +462,16 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         const double esbc = EMISFC * SBC;
         const double u0 = FWIND0 * ua8, v0 = FWIND0 * va8;
         const double gtemp0 = 1.0 - FTEMP0, rcp = 1.0 / CP;
-        const double dt1 = c_T.wvi[KX - 1][1] * (ta[7] - ta[6]);
-        double t1l = ta[7] + dt1;
+        const double dt1 = c_T.wvi[KX - 1][1] * (ta7 - ta6);
+        double t1l = ta7 + dt1;
         double t1s = t1l - phi0 * dt1 / (RGAS * FL(288.0) * c_T.sigl[KX - 1]);
-        const double t2s = ta[7] + rcp * phi[7];
+        const double t2s = ta7 + rcp * phi7;
         const double t2l = t2s - rcp * phi0;
-        if (ta[7] > ta[6]) {
+        if (ta7 > ta6) {
             t1l = FTEMP0 * t1l + gtemp0 * t2l;
             t1s = FTEMP0 * t1s + gtemp0 * t2s;
         } else {
-            t1l = ta[7], t1s = ta[7];
+            t1l = ta7, t1s = ta7;
         }
         const double t0 = t1s + fmask * (t1l - t1s);
         const double denvvs0 = (P0 * psa / (RGAS * t0)) * sqrt(u0 * u0 + v0 * v0 + VGUST * VGUST);
@@ -413,7 +483,7 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         const double ustr1 = -cdldv * ua8, vstr1 = -cdldv * va8;
         const double chlcp = CHL * CP;
         double shf1 = chlcp * denvvs1 * (tskin - t1l);
-        const double q1 = qa[7];
+        const double q1 = qa7;
         const double qsat01 = qsat_of(tskin, psa, 1.0);
         double evap1 = CHL * denvvs1 * fmax(0.0, saw * qsat01 - q1);
         const double tsk3 = pow(tskin, 3.0);
@@ -469,7 +539,7 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
         for (int jb = 0; jb < 4; jb++)
 #pragma unroll
             for (int k = KX - 1; k >= 1; k--) {
-                const double tk = tau2[(k + KX * jb) * lev];
+                const double tk = tau[jb][k];
                 const double emis = 1.0 - tk;
                 const double brad = fband_at(fb, ta[k], jb) * (st4a1[k] - emis * st4a2[k]);
                 dfabs[k] = dfabs[k] + flux[jb];
@@ -478,7 +548,7 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
             }
 #pragma unroll
         for (int jb = 0; jb < 2; jb++) {
-            const double tk = tau2[(0 + KX * jb) * lev];
+            const double tk = tau[jb][0];
             const double emis = 1.0 - tk;
             const double brad = fband_at(fb, ta[0], jb) * (st4a1[0] - emis * st4a2[0]);
             dfabs[0] = dfabs[0] + flux[jb];
@@ -503,79 +573,19 @@ __global__ void __launch_bounds__(128) k_physics(const Ctx c, const ScratchLayou
             for (int k = 0; k < KX; k++) ps4[k * lev] = st4a1[k], ps4[(k + KX) * lev] = st4a2[k];
         }
     }
-    // physics.f90:200-204: ttend = ttend + tt_rsw + tt_rlw
-#pragma unroll
-    for (int k = 0; k < KX; k++) ottend[k * lev] = (ottend[k * lev] + ttrsw[k * lev]) + dfabs[k] * rps * c_T.grdscp[k];
-
-    // ---- vertical diffusion and shallow convection (vertical_diffusion.f90:30-146)
+    // physics.f90:200-204: ttend = ttend + tt_rsw + tt_rlw ; :214-231: + surface fluxes and PBL tendencies
     {
-        const double trshc = FL(6.0), trvdi = FL(24.0), trvds = FL(6.0), redshc = FL(0.5), rhgrad = FL(0.5), segrad = FL(0.1);
-        const double cshc = c_T.dhs[7] / FL(3600.0);
-        const double cvdi = (c_T.sigh[7] - c_T.sigh[1]) / (double)(6.0f * 3600.0f);
-        const double fshcq = cshc / trshc, fshcse = cshc / (trshc * CP);
-        const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * CP);
-        double tv[KX], qv[KX];
-#pragma unroll
-        for (int k = 0; k < KX; k++) tv[k] = 0.0, qv[k] = 0.0;
-        const double rsig6 = 1.0 / c_T.dhs[6], rsig7 = 1.0 / c_T.dhs[7];
-        {
-            const double drh0 = rhgrad * (c_T.fsg[7] - c_T.fsg[6]);
-            const double fvdiq2 = fvdiq * c_T.sigh[7];
-            const double dmse = se[7] - se[6] + ALHC * (qa[7] - qsat[6]);
-            const double drh = rh[7] - rh[6];
-            double fcnv = 1.0;
-            if (dmse >= 0.0) {
-                if (icnv > 0) fcnv = redshc;
-                const double fluxse = fcnv * fshcse * dmse;
-                tv[6] = fluxse * rsig6;
-                tv[7] = -fluxse * rsig7;
-                if (drh >= 0.0) {
-                    const double fluxq = fcnv * fshcq * qsat[7] * drh;
-                    qv[6] = fluxq * rsig6;
-                    qv[7] = -fluxq * rsig7;
-                }
-            } else if (drh > drh0) {
-                const double fluxq = fvdiq2 * qsat[6] * drh;
-                qv[6] = fluxq * rsig6;
-                qv[7] = -fluxq * rsig7;
-            }
-        }
-#pragma unroll
-        for (int k = 3; k <= KX - 2; k++)  // 1-based k
-            if (c_T.sigh[k] > 0.5) {
-                const double drh0 = rhgrad * (c_T.fsg[k] - c_T.fsg[k - 1]);
-                const double fvdiq2 = fvdiq * c_T.sigh[k];
-                const double drh = rh[k] - rh[k - 1];
-                if (drh >= drh0) {
-                    const double fluxq = fvdiq2 * qsat[k - 1] * drh;
-                    qv[k - 1] = qv[k - 1] + fluxq * (1.0 / c_T.dhs[k - 1]);
-                    qv[k] = qv[k] - fluxq * (1.0 / c_T.dhs[k]);
-                }
-            }
-#pragma unroll
-        for (int k = 0; k < KX - 1; k++) {
-            const double se0 = se[k + 1] + segrad * (phi[k] - phi[k + 1]);
-            if (se[k] < se0) {
-                const double fluxse = fvdise * (se0 - se[k]);
-                tv[k] = tv[k] + fluxse * (1.0 / c_T.dhs[k]);
-                const double r1 = 1.0 / (1.0 - c_T.sigh[k + 1]);
-#pragma unroll
-                for (int k1 = k + 1; k1 < KX; k1++) tv[k1] = tv[k1] - fluxse * r1;
-            }
-        }
-        // physics.f90:214-223: surface-flux tendencies at the lowest level, then add
         const double utp = 0.0 + ustr3 * rps * c_T.grdsig[7], vtp = 0.0 + vstr3 * rps * c_T.grdsig[7];
         tv[7] = tv[7] + shf3 * rps * c_T.grdscp[7];
         qv[7] = qv[7] + evap3 * rps * c_T.grdsig[7];
         double *outend = scp(c, t, L.utend, lane) + e + 7 * lev, *ovtend = scp(c, t, L.vtend, lane) + e + 7 * lev;
         *outend = *outend + utp;
         *ovtend = *ovtend + vtp;
+        oqtend[7 * lev] = qsum[7] + qv[7];
 #pragma unroll
-        for (int k = 0; k < KX; k++) {
-            ottend[k * lev] = ottend[k * lev] + tv[k];
-            oqtend[k * lev] = oqtend[k * lev] + qv[k];
-        }
+        for (int k = 0; k < KX; k++) ottend[k * lev] = ((tsum[k] + trsw_s[k]) + dfabs[k] * rps * c_T.grdscp[k]) + tv[k];
     }
+
     if (dbg) {
         int *d = dbg + ((size_t)t * 3 * NG + q) * TILE + lane;
         d[0] = itop, d[(size_t)NG * TILE] = icnv, d[(size_t)2 * NG * TILE] = icltop_out;

@@ -108,6 +108,7 @@ struct ScratchLayout {
     long long sfwd;                                  // 73 forward-transform outputs
     // Fourier fields (62 x 48)
     long long four;                                  // max(77, 73) fields
+    long long diagp;                                 // partial sums of the diagnostics check
     long long total;
 };
 ScratchLayout make_scratch_layout();

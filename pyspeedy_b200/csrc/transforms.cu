@@ -138,7 +138,7 @@ struct StGrid {
     __device__ __forceinline__ void operator()(int i, double v) const { p[i * TILE] = v * sc; }
 };
 
-__global__ void __launch_bounds__(128) k_fft_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off,
+__global__ void __launch_bounds__(128, 4) k_fft_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off,
                                                  int nlg) {
     __shared__ double sm[2 * IX * TILE];  // 48 KB: exchange buffers of 2 line-groups
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
