@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libspeedy_b200.so")
+LIB_PATH = os.environ.get("SPDY_LIB", os.path.join(_HERE, "csrc", "libspeedy_b200.so"))
 
 with open(os.path.join(_HERE, "data", "model_state.json")) as _fp:
     REGISTRY = json.load(_fp)

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
 
 // Divergence, temperature, log(ps): coupled in the vertical by the semi-implicit scheme -> one thread per
 // (coefficient, component) holding the 8-level columns (tendencies.f90:283-352, implicit.f90:234-289)
+template <bool CT>  // CT: implicit matrices from __constant__ memory (regular step); else from global (first_step)
 __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const ScratchLayout L, const int j1, const double dt,
                                                       const double eps, const int impl_idx) {
     const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
         for (int k = 0; k < KX; k++) {
             double ye = 0.0;
 #pragma unroll
-            for (int k1 = 0; k1 < KX; k1++) ye = ye + I->xd[k + KX * k1] * tdt[k1];
+            for (int k1 = 0; k1 < KX; k1++) ye = ye + (CT ? c_T.xd2[k + KX * k1] : I->xd[k + KX * k1]) * tdt[k1];
             ye = ye + (D_RGAS * c_T.tref[k]) * psdt;
             yf[k] = divdt[k] + elz * ye;
         }
@@ -251,18 +252,18 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
 #pragma unroll
         for (int k = 0; k < KX; k++) divdt[k] = 0.0;
         if (l != 0) {
-            const double *xj = I->xj + (size_t)KX * KX * (l - 1);
+            const double *xj = (CT ? c_T.xj2 : I->xj) + (size_t)KX * KX * (l - 1);
 #pragma unroll
             for (int k1 = 0; k1 < KX; k1++)
 #pragma unroll
                 for (int k = 0; k < KX; k++) divdt[k] = divdt[k] + xj[k + KX * k1] * yf[k1];
         }
 #pragma unroll
-        for (int k = 0; k < KX; k++) psdt = psdt - divdt[k] * I->dhsx[k];
+        for (int k = 0; k < KX; k++) psdt = psdt - divdt[k] * (CT ? c_T.dhsx2[k] : I->dhsx[k]);
 #pragma unroll
         for (int k = 0; k < KX; k++)
 #pragma unroll
-            for (int k1 = 0; k1 < KX; k1++) tdt[k] = tdt[k] + I->xc[k + KX * k1] * divdt[k1];
+            for (int k1 = 0; k1 < KX; k1++) tdt[k] = tdt[k] + (CT ? c_T.xc2[k + KX * k1] : I->xc[k + KX * k1]) * divdt[k1];
     }
     // ---- D/E. horizontal diffusion, stratospheric drag and time integration (time_stepping.f90:78-144)
     const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
@@ -382,7 +383,8 @@ void launch_grid_dyn(cudaStream_t s, const Ctx &c, const ScratchLayout &L) {
 }
 void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j1, double dt, double eps, int impl_idx) {
     k_spec_step_vq<<<dim3(NSPC * 2 * KX / 8, c.ntiles), 256, 0, s>>>(c, L, j1, dt, eps, impl_idx);
-    k_spec_step_dt<<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+    if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+    else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
 }
 void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part) {
     k_diag_partial<<<dim3(KX * (MX - 1), c.ntiles), 32, 0, s>>>(c, time_lev, part);

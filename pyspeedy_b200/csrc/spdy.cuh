@@ -38,6 +38,9 @@ struct ConstTables {
     double tref[KX], tref2[KX], tref3[KX], tcorv[KX], qcorv[KX], xgeop1[KX], xgeop2[KX];
     double coriol[IL], sia[IL], coa[IL], cosgr[IL], cosgr2[IL], radang[IL], wt[IY];
     double geocorf[KX];  // lapse-rate correction factors of get_geopotential (k = 2..kx-1)
+    // semi-implicit matrices for the regular leapfrog step (dt = 2*delt): constant-bank operands of the 8x8
+    // mat-vecs in k_spec_step_dt (implicit.f90:234-289)
+    double xc2[KX * KX], xd2[KX * KX], xj2[KX * KX * 64], dhsx2[KX];
 };
 
 // ---- larger tables in global memory (warp-uniform loads) ---------------------------------------------------

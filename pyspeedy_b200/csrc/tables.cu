@@ -349,6 +349,10 @@ void build_tables(ConstTables &C, GlobTables &G) {
     build_impl(C, G, 0.5 * H_DELT, G.impl[0]);
     build_impl(C, G, H_DELT, G.impl[1]);
     build_impl(C, G, 2.0 * H_DELT, G.impl[2]);
+    memcpy(C.xc2, G.impl[2].xc, sizeof(C.xc2));
+    memcpy(C.xd2, G.impl[2].xd, sizeof(C.xd2));
+    memcpy(C.xj2, G.impl[2].xj, sizeof(C.xj2));
+    memcpy(C.dhsx2, G.impl[2].dhsx, sizeof(C.dhsx2));
 }
 
 }  // namespace spdy
