@@ -1,0 +1,88 @@
+"""Host-side logic that needs no GPU: C ABI surface, driver mirror, dataset/NetCDF output, sharding maths."""
+import ctypes
+import os
+import re
+from datetime import datetime
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol(drv):
+    hdr = open(os.path.join(ROOT, "include", "speedy_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(spdy_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 30
+    lib = ctypes.CDLL(drv.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_driver_surface_matches_reference_names(drv):
+    """The f2py module exposes get_/set_/is_array_ for all 109 variables and _shape for the 102 arrays."""
+    d = drv.speedy_driver
+    reg = drv.REGISTRY
+    assert len(reg) == 109
+    arrays = [e for e in reg if e["shape"] is not None]
+    assert len(arrays) == 102
+    for e in reg:
+        for pre in ("get_", "set_", "is_array_"):
+            assert hasattr(d, pre + e["name"]), pre + e["name"]
+    for e in arrays:
+        assert hasattr(d, f"get_{e['name']}_shape")
+        assert getattr(d, f"is_array_{e['name']}")() is True
+    for n in ("modelstate_init", "modelstate_init_sst_anom", "modelstate_close", "controlparams_init",
+              "controlparams_close", "create_datetime", "get_datetime", "close_datetime", "init", "step",
+              "parallel_step", "check", "transform_spectral2grid", "transform_grid2spectral", "apply_grid_filter"):
+        assert hasattr(d, n), n
+    assert d.is_array_current_step() is False
+
+
+def test_registry_header_consistent(drv):
+    hdr = open(os.path.join(ROOT, "include", "spdy_registry.h")).read()
+    for e in drv.REGISTRY:
+        assert f"V_{e['name']} = {e['id']}," in hdr
+
+
+def test_dataset_roundtrip(tmp_path):
+    from pyspeedy_b200.dataset import Dataset
+
+    rng = np.random.default_rng(0)
+    t = datetime(1982, 1, 2)
+
+    def member(k):
+        dv = {"t": (["lon", "lat", "lev", "time", "ens"], rng.standard_normal((96, 48, 8, 1, 1)).astype(np.float32))}
+        co = dict(lon=np.arange(96, dtype=np.float32), lat=np.arange(48, dtype=np.float32), lev=np.arange(8, dtype=np.float32),
+                  time=[t], ens=[k])
+        return Dataset(dv, co).reverse("lev").transpose("time", "ens", "lev", "lat", "lon")
+
+    a, b = member(0), member(1)
+    m = Dataset.merge([a, b])
+    assert m["t"].shape == (1, 2, 8, 48, 96)
+    assert np.array_equal(m.sel_ens(1)["t"], b["t"][:, 0])
+    assert m["lev"][0] == 7.0
+    p = tmp_path / "x.nc"
+    m.to_netcdf(str(p))
+    r = Dataset.open_dataset(str(p))
+    assert r.dims("t") == ("time", "ens", "lev", "lat", "lon")
+    assert np.array_equal(r["t"], m["t"]) and r.coords["time"] == [t]
+
+
+def test_month_window_arithmetic():
+    from pyspeedy_b200.speedy import _add_months
+
+    assert _add_months(datetime(1982, 1, 1), -1) == datetime(1981, 12, 1)
+    assert _add_months(datetime(1982, 12, 1), 1) == datetime(1983, 1, 1)
+    assert _add_months(datetime(1982, 5, 1), 8) == datetime(1983, 1, 1)
+
+
+def test_bench_algorithmic_bytes():
+    """DESIGN.md section 5 / SURVEY 8(d): the per-unit byte counts the roofline is computed from."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.SPEC_B == 31 * 32 * 16 and b.GRID_B == 96 * 48 * 8 and b.FOUR_B == 62 * 48 * 8
+    assert b.ALG_BYTES["legendre_inv"] == 77 * 39680 and b.ALG_BYTES["fft_inv"] == 77 * 60672
