@@ -249,9 +249,17 @@ def run_b200(args):
     cls = max(ALG_BYTES, key=lambda k: prof[k])
     achieved = ALG_BYTES[cls] * n_prof / (prof[cls] * 1e-3) / 1e9
     total_prof = sum(prof.values())
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same launch size)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fp:
+            tj = json.load(fp)
+        if tj["members_per_launch"] == n_prof:
+            traffic = tj["bytes"].get(cls)
     roofline = {
         "bound": "hbm", "kernel": cls, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES[cls] * n_prof,
+        "peak_kind": peak_kind,
         "share_of_step": prof[cls] / total_prof,
         "per_class_ms": {k: round(v, 4) for k, v in prof.items()},
         "per_class_gbs": {k: round(ALG_BYTES[k] * n_prof / (prof[k] * 1e-3) / 1e9, 1) for k in ALG_BYTES if prof[k] > 0},
