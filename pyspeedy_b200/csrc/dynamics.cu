@@ -112,26 +112,20 @@ __device__ __forceinline__ void vdspec_elem(const GlobTables *G, const double *s
     }
 }
 
-// Same operator for ONE component (cc = 0 real, 1 imaginary).  su/sv point at the (m,n) element of this component;
-// the i*gradx term needs the other component of the centre element only: `oth` = +TILE (cc = 0) or -TILE (cc = 1).
-// WANT: 1 = vorticity only, 2 = divergence only, 3 = both.
+// Same operator for ONE component (cc = 0 real, 1 imaginary), branch-free so that the loads of all levels can be
+// issued together.  su/sv point at the (m,n) element of this component; the i*gradx term needs the other component of
+// the centre element only (`oth` = +TILE / -TILE).  The special rows n = 1 and n = nx of spectral.f90:171-176 are
+// the general row with exact zeros: vddym(m,1) = 0 and vddyp(m,nx) = 0 in the tables (spectral.f90:98-99,110 with
+// epsi(:,nx+1) = 0), the neighbour that does not exist is replaced by the element itself (multiplied by that zero),
+// and row nx has no i*gradx term (zsel = 0).  WANT: 1 = vorticity, 2 = divergence.
 template <int WANT>
 __device__ __forceinline__ void vdspec_comp(const double gx, const double ym, const double yp, const double *su,
                                             const double *sv, const int n, const int cc, double &vor, double &dv) {
-    const long long up = (long long)M2 * TILE, oth = cc ? -TILE : TILE;
-    // (a+bi)*i = -b + ai : real part uses -imag, imaginary part uses +real
-    if (WANT & 1) {
-        const double zc = cc ? gx * sv[oth] : -(gx * sv[oth]);
-        if (n == 0) vor = zc - yp * su[up];
-        else if (n == NX - 1) vor = ym * su[-up];
-        else vor = (ym * su[-up] - yp * su[up]) + zc;
-    }
-    if (WANT & 2) {
-        const double zp = cc ? gx * su[oth] : -(gx * su[oth]);
-        if (n == 0) dv = zp + yp * sv[up];
-        else if (n == NX - 1) dv = (-ym) * sv[-up];
-        else dv = ((-ym) * sv[-up] + yp * sv[up]) + zp;
-    }
+    const long long up = (n == NX - 1) ? 0 : (long long)M2 * TILE, dn = (n == 0) ? 0 : -(long long)M2 * TILE;
+    const long long oth = cc ? -TILE : TILE;
+    const double zsel = (n == NX - 1) ? 0.0 : (cc ? gx : -gx);  // (a+bi)*i = -b + ai
+    if (WANT & 1) vor = (ym * su[dn] - yp * su[up]) + zsel * sv[oth];
+    if (WANT & 2) dv = ((-ym) * sv[dn] + yp * sv[up]) + zsel * su[oth];
 }
 
 // leapfrog + Robert-Asselin-Williams filter on one component (time_stepping.f90:164-188)

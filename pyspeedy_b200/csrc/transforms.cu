@@ -30,7 +30,7 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
         double er[6], ei[6], orr[6], oi[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) er[q] = ei[q] = orr[q] = oi[q] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int n0 = 0; n0 <= nmax; n0 += 2) {  // even parity: l - m even
             const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
             const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
@@ -39,7 +39,7 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
             er[2] += xr * p1.x, ei[2] += xi * p1.x, er[3] += xr * p1.y, ei[3] += xi * p1.y;
             er[4] += xr * p2.x, ei[4] += xi * p2.x, er[5] += xr * p2.y, ei[5] += xi * p2.y;
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int n0 = 1; n0 <= nmax; n0 += 2) {  // odd parity
             const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
             const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
@@ -94,27 +94,25 @@ __global__ void __launch_bounds__(128) k_legendre_dir(const Ctx c, const FwdOut 
             od[j] = (fn - fs) * c_T.wt[j];
         }
 #pragma unroll 1
-        for (int n0 = 0; n0 < NX; n0++) {
-            double acc = 0.0;
-            if (n0 <= nmax) {
-                const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY);
-                if ((n0 & 1) == 0) {
+        for (int n0 = 0; n0 < NX; n0 += 2) {  // n0 even -> even parity (ev), n0 + 1 -> odd parity (od): two chains
+            double acc0 = 0.0, acc1 = 0.0;
+            const double2 *p0 = reinterpret_cast<const double2 *>(Pm + n0 * IY), *p1 = p0 + IY / 2;
+            const bool on0 = n0 <= nmax, on1 = n0 + 1 <= nmax;
+            if (on0) {
 #pragma unroll
-                    for (int j = 0; j < IY; j += 2) {
-                        const double2 pp = __ldg(p + (j >> 1));
-                        acc += pp.x * ev[j];
-                        acc += pp.y * ev[j + 1];
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < IY; j += 2) {
-                        const double2 pp = __ldg(p + (j >> 1));
-                        acc += pp.x * od[j];
-                        acc += pp.y * od[j + 1];
+                for (int j = 0; j < IY; j += 2) {
+                    const double2 a = __ldg(p0 + (j >> 1));
+                    acc0 += a.x * ev[j];
+                    acc0 += a.y * ev[j + 1];
+                    if (on1) {
+                        const double2 b = __ldg(p1 + (j >> 1));
+                        acc1 += b.x * od[j];
+                        acc1 += b.y * od[j + 1];
                     }
                 }
             }
-            X[((size_t)n0 * M2 + 2 * m0 + cc) * TILE] = acc;
+            X[((size_t)n0 * M2 + 2 * m0 + cc) * TILE] = acc0;
+            X[((size_t)(n0 + 1) * M2 + 2 * m0 + cc) * TILE] = acc1;
         }
     }
 }
