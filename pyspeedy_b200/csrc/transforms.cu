@@ -16,6 +16,9 @@ namespace spdy {
 
 
 #define FFT_LS TILE
+#ifndef FFT_MINBLOCKS
+#define FFT_MINBLOCKS 3
+#endif
 #include "fft96_gen.cuh"
 
 // ------------------------------------------------------------------------------------------- Legendre inverse
@@ -32,7 +35,7 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
         for (int q = 0; q < 6; q++) er[q] = ei[q] = orr[q] = oi[q] = 0.0;
 #pragma unroll 4
         for (int n0 = 0; n0 <= nmax; n0 += 2) {  // even parity: l - m even
-            const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
+            const double xr = __ldg(Xr + (size_t)n0 * M2 * TILE), xi = __ldg(Xi + (size_t)n0 * M2 * TILE);
             const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
             const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
             er[0] += xr * p0.x, ei[0] += xi * p0.x, er[1] += xr * p0.y, ei[1] += xi * p0.y;
@@ -41,7 +44,7 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
         }
 #pragma unroll 4
         for (int n0 = 1; n0 <= nmax; n0 += 2) {  // odd parity
-            const double xr = Xr[(size_t)n0 * M2 * TILE], xi = Xi[(size_t)n0 * M2 * TILE];
+            const double xr = __ldg(Xr + (size_t)n0 * M2 * TILE), xi = __ldg(Xi + (size_t)n0 * M2 * TILE);
             const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
             const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
             orr[0] += xr * p0.x, oi[0] += xi * p0.x, orr[1] += xr * p0.y, oi[1] += xi * p0.y;
@@ -94,41 +97,36 @@ __global__ void __launch_bounds__(128) k_legendre_dir(const Ctx c, const FwdOut 
             od[j] = (fn - fs) * c_T.wt[j];
         }
 #pragma unroll 1
-        for (int n0 = 0; n0 < NX; n0 += 2) {  // n0 even -> even parity (ev), n0 + 1 -> odd parity (od): two chains
-            double acc0 = 0.0, acc1 = 0.0;
-            const double2 *p0 = reinterpret_cast<const double2 *>(Pm + n0 * IY), *p1 = p0 + IY / 2;
-            const bool on0 = n0 <= nmax, on1 = n0 + 1 <= nmax;
-            if (on0) {
+        for (int n0 = 0; n0 < NX; n0 += 4) {  // n0, n0+2 even parity (ev) ; n0+1, n0+3 odd parity (od): four chains
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY);
+            if (n0 <= nmax) {  // rows beyond the mask keep acc = 0 (P is not read: table rows exist up to n = 31)
+                const double w1 = (n0 + 1 <= nmax) ? 1.0 : 0.0, w2 = (n0 + 2 <= nmax) ? 1.0 : 0.0,
+                             w3 = (n0 + 3 <= nmax) ? 1.0 : 0.0;
 #pragma unroll
                 for (int j = 0; j < IY; j += 2) {
-                    const double2 a = __ldg(p0 + (j >> 1));
-                    acc0 += a.x * ev[j];
-                    acc0 += a.y * ev[j + 1];
-                    if (on1) {
-                        const double2 b = __ldg(p1 + (j >> 1));
-                        acc1 += b.x * od[j];
-                        acc1 += b.y * od[j + 1];
-                    }
+                    const double2 a0 = __ldg(p + (j >> 1)), a1 = __ldg(p + IY / 2 + (j >> 1)),
+                                  a2 = __ldg(p + IY + (j >> 1)), a3 = __ldg(p + 3 * IY / 2 + (j >> 1));
+                    acc[0] += a0.x * ev[j], acc[1] += a1.x * od[j], acc[2] += a2.x * ev[j], acc[3] += a3.x * od[j];
+                    acc[0] += a0.y * ev[j + 1], acc[1] += a1.y * od[j + 1], acc[2] += a2.y * ev[j + 1],
+                        acc[3] += a3.y * od[j + 1];
                 }
+                acc[1] *= w1, acc[2] *= w2, acc[3] *= w3;  // exact: masks are 0 or 1
             }
-            X[((size_t)n0 * M2 + 2 * m0 + cc) * TILE] = acc0;
-            X[((size_t)(n0 + 1) * M2 + 2 * m0 + cc) * TILE] = acc1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) X[((size_t)(n0 + q) * M2 + 2 * m0 + cc) * TILE] = acc[q];
         }
     }
 }
 
 // ----------------------------------------------------------------------------------------------- inverse FFT
-// Static schedule of the 14 stage-A items (2 line-groups x 7) over 4 warps, balanced by flop count
-// (A0: 24, A1..A5: 96, A6: 36).  Entry = line_group * 8 + item ; 255 = none.
-__constant__ unsigned char c_schedA[4][4] = {
-    {0 * 8 + 1, 0 * 8 + 2, 0 * 8 + 3, 255},
-    {0 * 8 + 4, 0 * 8 + 5, 1 * 8 + 1, 255},
-    {1 * 8 + 2, 1 * 8 + 3, 0 * 8 + 0, 0 * 8 + 6},
-    {1 * 8 + 4, 1 * 8 + 5, 1 * 8 + 0, 1 * 8 + 6}};
-
+// CTA = 4 warps x 2 line-groups (a line-group = 32 members x one latitude of one field).  Every warp has a STATIC
+// list of stage-A items (balanced by flop count: A0 24, A1..A5 96, A6 36) written out as straight-line code, so all
+// of its global loads (read-only path) are independent of each other and of the shared-memory stores and can be in
+// flight together; one barrier; then a static list of stage-B items.
 struct LdFour {
     const double *p;
-    __device__ __forceinline__ double operator()(int r) const { return p[r * TILE]; }
+    __device__ __forceinline__ double operator()(int r) const { return __ldg(p + r * TILE); }
 };
 struct StGrid {
     double *p;
@@ -136,50 +134,36 @@ struct StGrid {
     __device__ __forceinline__ void operator()(int i, double v) const { p[i * TILE] = v * sc; }
 };
 
-__global__ void __launch_bounds__(128, 4) k_fft_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off,
-                                                 int nlg) {
+__global__ void __launch_bounds__(128, FFT_MINBLOCKS) k_fft_inv(const Ctx c, const InvDesc *__restrict__ descs,
+                                                                 long long four_off, int nlg) {
     __shared__ double sm[2 * IX * TILE];  // 48 KB: exchange buffers of 2 line-groups
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.y, lg0 = blockIdx.x * 2;
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-        const int e = c_schedA[warp][r];
-        if (e == 255) continue;
-        const int g = e >> 3, item = e & 7, lg = lg0 + g;
-        if (lg >= nlg) continue;
-        const int f = lg / IL, j = lg - f * IL;
-        const LdFour ld{scp(c, t, four_off + (long long)f * NFOUR + j * M2, lane)};
-        double *s = sm + g * IX * TILE + lane;
-        switch (item) {
-            case 0: fftb_A0(ld, s); break;
-            case 1: fftb_A1(ld, s); break;
-            case 2: fftb_A2(ld, s); break;
-            case 3: fftb_A3(ld, s); break;
-            case 4: fftb_A4(ld, s); break;
-            case 5: fftb_A5(ld, s); break;
-            default: fftb_A6(ld, s); break;
-        }
+    const int t = blockIdx.y, lg0 = blockIdx.x * 2;  // nlg is even (48 latitudes per field)
+    const int f0 = lg0 / IL, j0 = lg0 - f0 * IL, f1 = (lg0 + 1) / IL, j1 = (lg0 + 1) - f1 * IL;
+    const LdFour ld0{scp(c, t, four_off + (long long)f0 * NFOUR + j0 * M2, lane)};
+    const LdFour ld1{scp(c, t, four_off + (long long)f1 * NFOUR + j1 * M2, lane)};
+    double *s0 = sm + lane, *s1 = sm + IX * TILE + lane;
+    if (warp == 0) {
+        fftb_A1(ld0, s0), fftb_A2(ld0, s0), fftb_A3(ld0, s0);
+    } else if (warp == 1) {
+        fftb_A4(ld0, s0), fftb_A5(ld0, s0), fftb_A1(ld1, s1);
+    } else if (warp == 2) {
+        fftb_A2(ld1, s1), fftb_A3(ld1, s1), fftb_A0(ld0, s0), fftb_A6(ld0, s0);
+    } else {
+        fftb_A4(ld1, s1), fftb_A5(ld1, s1), fftb_A0(ld1, s1), fftb_A6(ld1, s1);
     }
     __syncthreads();
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-        const int e = warp + 4 * r;  // 16 stage-B items
-        const int g = e >> 3, item = e & 7, lg = lg0 + g;
-        if (lg >= nlg) continue;
-        const int f = lg / IL, j = lg - f * IL;
-        const InvDesc d = descs[f];
-        const StGrid st{scp(c, t, d.dst + (long long)j * IX, lane), d.kcos == 1 ? 1.0 : c_T.cosgr[j]};
-        const double *s = sm + g * IX * TILE + lane;
-        switch (item) {
-            case 0: fftb_B0(s, st); break;
-            case 1: fftb_B1(s, st); break;
-            case 2: fftb_B2(s, st); break;
-            case 3: fftb_B3(s, st); break;
-            case 4: fftb_B4(s, st); break;
-            case 5: fftb_B5(s, st); break;
-            case 6: fftb_B6(s, st); break;
-            default: fftb_B7(s, st); break;
-        }
+    const InvDesc d0 = descs[f0], d1 = descs[f1];
+    const StGrid st0{scp(c, t, d0.dst + (long long)j0 * IX, lane), d0.kcos == 1 ? 1.0 : c_T.cosgr[j0]};
+    const StGrid st1{scp(c, t, d1.dst + (long long)j1 * IX, lane), d1.kcos == 1 ? 1.0 : c_T.cosgr[j1]};
+    if (warp == 0) {
+        fftb_B0(s0, st0), fftb_B1(s0, st0), fftb_B2(s0, st0), fftb_B3(s0, st0);
+    } else if (warp == 1) {
+        fftb_B4(s0, st0), fftb_B5(s0, st0), fftb_B6(s0, st0), fftb_B7(s0, st0);
+    } else if (warp == 2) {
+        fftb_B0(s1, st1), fftb_B1(s1, st1), fftb_B2(s1, st1), fftb_B3(s1, st1);
+    } else {
+        fftb_B4(s1, st1), fftb_B5(s1, st1), fftb_B6(s1, st1), fftb_B7(s1, st1);
     }
 }
 
@@ -190,14 +174,14 @@ template <int MODE> struct LdGrid {
     const double *a, *b;
     double k0, sc;
     __device__ __forceinline__ double operator()(int i) const {
-        if (MODE == FM_PLAIN) return a[i * TILE];
-        if (MODE == FM_COS) return a[i * TILE] * sc;
+        if (MODE == FM_PLAIN) return __ldg(a + i * TILE);
+        if (MODE == FM_COS) return __ldg(a + i * TILE) * sc;
         if (MODE == FM_KE) {
-            const double u = a[i * TILE], v = b[i * TILE];
+            const double u = __ldg(a + i * TILE), v = __ldg(b + i * TILE);
             return 0.5 * (u * u + v * v);
         }
-        if (MODE == FM_FLUXT) return (-a[i * TILE] * (b[i * TILE] - k0)) * sc;
-        return (-a[i * TILE] * b[i * TILE]) * sc;  // FM_FLUX
+        if (MODE == FM_FLUXT) return (-__ldg(a + i * TILE) * (__ldg(b + i * TILE) - k0)) * sc;
+        return (-__ldg(a + i * TILE) * __ldg(b + i * TILE)) * sc;  // FM_FLUX
     }
 };
 struct StFour {
@@ -206,64 +190,49 @@ struct StFour {
     __device__ __forceinline__ void operator()(int r, double v) const { p[r * TILE] = v * scale; }
 };
 
-// stage-B items of the forward transform: B0: 21, B1..B5: 102, B6: 34 flops ; 14 items over 4 warps
-__constant__ unsigned char c_schedFB[4][4] = {
-    {0 * 8 + 1, 0 * 8 + 2, 0 * 8 + 3, 255},
-    {0 * 8 + 4, 0 * 8 + 5, 1 * 8 + 1, 255},
-    {1 * 8 + 2, 1 * 8 + 3, 0 * 8 + 0, 0 * 8 + 6},
-    {1 * 8 + 4, 1 * 8 + 5, 1 * 8 + 0, 1 * 8 + 6}};
+template <int MODE>
+__device__ __forceinline__ LdGrid<MODE> make_ld(const Ctx &c, int t, const FwdDesc &d, int j, int lane) {
+    LdGrid<MODE> ld;
+    ld.a = refp(c, t, d.a, lane) + (size_t)j * IX * TILE;
+    ld.b = (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) ? refp(c, t, d.b, lane) + (size_t)j * IX * TILE : nullptr;
+    ld.k0 = d.k0;
+    ld.sc = (d.kcos == 3) ? c_T.cosgr2[j] : c_T.cosgr[j];
+    return ld;
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k_fft_fwd(const Ctx c, const FwdDesc *__restrict__ descs, long long four_off,
-                                                 int nlg) {
+__global__ void __launch_bounds__(128, FFT_MINBLOCKS) k_fft_fwd(const Ctx c, const FwdDesc *__restrict__ descs,
+                                                                 long long four_off, int nlg) {
     __shared__ double sm[2 * IX * TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.y, lg0 = blockIdx.x * 2;
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-        const int e = warp + 4 * r;
-        const int g = e >> 3, item = e & 7, lg = lg0 + g;
-        if (lg >= nlg) continue;
-        const int f = lg / IL, j = lg - f * IL;
-        const FwdDesc d = descs[f];
-        LdGrid<MODE> ld;
-        ld.a = refp(c, t, d.a, lane) + (size_t)j * IX * TILE;
-        ld.b = (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) ? refp(c, t, d.b, lane) + (size_t)j * IX * TILE : nullptr;
-        ld.k0 = d.k0;
-        ld.sc = (d.kcos == 3) ? c_T.cosgr2[j] : c_T.cosgr[j];
-        double *s = sm + g * IX * TILE + lane;
-        switch (item) {
-            case 0: fftf_A0(ld, s); break;
-            case 1: fftf_A1(ld, s); break;
-            case 2: fftf_A2(ld, s); break;
-            case 3: fftf_A3(ld, s); break;
-            case 4: fftf_A4(ld, s); break;
-            case 5: fftf_A5(ld, s); break;
-            case 6: fftf_A6(ld, s); break;
-            default: fftf_A7(ld, s); break;
-        }
+    const int f0 = lg0 / IL, j0 = lg0 - f0 * IL, f1 = (lg0 + 1) / IL, j1 = (lg0 + 1) - f1 * IL;
+    const FwdDesc d0 = descs[f0], d1 = descs[f1];
+    double *s0 = sm + lane, *s1 = sm + IX * TILE + lane;
+    if (warp < 2) {  // stage A: 8 equal items per line-group, 4 per warp
+        const LdGrid<MODE> ld = make_ld<MODE>(c, t, d0, j0, lane);
+        if (warp == 0) fftf_A0(ld, s0), fftf_A1(ld, s0), fftf_A2(ld, s0), fftf_A3(ld, s0);
+        else fftf_A4(ld, s0), fftf_A5(ld, s0), fftf_A6(ld, s0), fftf_A7(ld, s0);
+    } else {
+        const LdGrid<MODE> ld = make_ld<MODE>(c, t, d1, j1, lane);
+        if (warp == 2) fftf_A0(ld, s1), fftf_A1(ld, s1), fftf_A2(ld, s1), fftf_A3(ld, s1);
+        else fftf_A4(ld, s1), fftf_A5(ld, s1), fftf_A6(ld, s1), fftf_A7(ld, s1);
     }
     __syncthreads();
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-        const int e = c_schedFB[warp][r];
-        if (e == 255) continue;
-        const int g = e >> 3, item = e & 7, lg = lg0 + g;
-        if (lg >= nlg) continue;
-        const int f = lg / IL, j = lg - f * IL;
-        const FwdDesc d = descs[f];
-        double *four = scp(c, t, four_off + (long long)d.fidx * NFOUR + j * M2, lane);
-        const StFour st{four, c_T.fc[3]};
-        const double *s = sm + g * IX * TILE + lane;
-        switch (item) {
-            case 0: fftf_B0(s, st); four[TILE] = 0.0; break;  // item 0 owns row 0; Im(m=0) := 0, fourier.f90:117
-            case 1: fftf_B1(s, st); break;
-            case 2: fftf_B2(s, st); break;
-            case 3: fftf_B3(s, st); break;
-            case 4: fftf_B4(s, st); break;
-            case 5: fftf_B5(s, st); break;
-            default: fftf_B6(s, st); break;
-        }
+    // stage B: B0 21, B1..B5 102, B6 34 flops per line-group; item B0 owns row 0 and zeroes row 1 (Im of m = 0)
+    double *four0 = scp(c, t, four_off + (long long)d0.fidx * NFOUR + j0 * M2, lane);
+    double *four1 = scp(c, t, four_off + (long long)d1.fidx * NFOUR + j1 * M2, lane);
+    const StFour st0{four0, c_T.fc[3]}, st1{four1, c_T.fc[3]};
+    if (warp == 0) {
+        fftf_B1(s0, st0), fftf_B2(s0, st0), fftf_B3(s0, st0);
+    } else if (warp == 1) {
+        fftf_B4(s0, st0), fftf_B5(s0, st0), fftf_B1(s1, st1);
+    } else if (warp == 2) {
+        fftf_B2(s1, st1), fftf_B3(s1, st1), fftf_B0(s0, st0), fftf_B6(s0, st0);
+        four0[TILE] = 0.0;  // fourier.f90:117
+    } else {
+        fftf_B4(s1, st1), fftf_B5(s1, st1), fftf_B0(s1, st1), fftf_B6(s1, st1);
+        four1[TILE] = 0.0;
     }
 }
 
