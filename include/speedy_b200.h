@@ -92,6 +92,8 @@ int spdy_debug_physics(int64_t state, const double *ug8, const double *vg8, cons
 /* one raw leapfrog step(j1, j2, dt) of time_stepping.f90:38-147 without calendar/coupler; dt_kind 0: delt/2, 1: delt, 2: 2*delt */
 int spdy_debug_raw_step(int64_t state, int j1, int j2, int dt_kind);
 int spdy_debug_get_corh(int64_t state, double *tcorh, double *qcorh);
+/* tendencies as returned by get_tendencies(state, ..., j2) (tendencies.f90:11-39); the prognostics are not advanced */
+int spdy_debug_tendencies(int64_t state, int j2, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt);
 
 #ifdef __cplusplus
 }

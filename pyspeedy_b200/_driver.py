@@ -78,6 +78,7 @@ def lib():
         L.spdy_debug_physics.argtypes = [i64] + [vp] * 11
         L.spdy_debug_raw_step.argtypes = [i64, ci, ci, ci]
         L.spdy_debug_get_corh.argtypes = [i64, vp, vp]
+        L.spdy_debug_tendencies.argtypes = [i64, ci, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

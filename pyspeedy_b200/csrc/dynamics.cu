@@ -144,7 +144,7 @@ __device__ __forceinline__ void raw_update(double *p1, double *p2, double fdt, c
 // Vorticity and tracer: no vertical coupling -> one thread per (coefficient, component, level)
 // (tendencies.f90:238-268 spectral part, time_stepping.f90:78-144)
 __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const ScratchLayout L, const int j1, const double dt,
-                                                      const double eps, const int impl_idx) {
+                                                      const double eps, const int impl_idx, const long long dump) {
     const int lane = threadIdx.x & 31, w = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y;
     // w = ((q * 2 + cc) * KX + k)
     const int k = w % KX, cc = (w / KX) & 1, q = w / (2 * KX);
@@ -161,6 +161,11 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
     vdspec_comp<1>(gx, ym, yp, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, n, cc, vo, dum);
     vdspec_comp<2>(gx, ym, yp, F + (FW_UQ + k) * lev, F + (FW_VQ + k) * lev, n, cc, dum, dq);
     double trdt = dq + F[(FW_QT + k) * lev];
+    if (dump >= 0) {  // test hook: tendencies as returned by get_tendencies (tendencies.f90:11-39), state untouched
+        *(scp(c, t, dump + (long long)(0 + k) * NSP, lane) + e) = vo;
+        *(scp(c, t, dump + (long long)(25 + k) * NSP, lane) + e) = trdt;
+        return;
+    }
     const double v1 = *vor, q1 = *trs;
     const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
     double vordt = (vo - dmp * v1) * I->dmp1[q];
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
 // (coefficient, component) holding the 8-level columns (tendencies.f90:283-352, implicit.f90:234-289)
 template <bool CT>  // CT: implicit matrices from __constant__ memory (regular step); else from global (first_step)
 __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const ScratchLayout L, const int j1, const double dt,
-                                                      const double eps, const int impl_idx) {
+                                                      const double eps, const int impl_idx, const long long dump) {
     const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     const int cc = w & 1, q = w >> 1;
     if (q >= NSPC) return;
@@ -258,6 +263,15 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
         for (int k = 0; k < KX; k++)
 #pragma unroll
             for (int k1 = 0; k1 < KX; k1++) tdt[k] = tdt[k] + (CT ? c_T.xc2[k + KX * k1] : I->xc[k + KX * k1]) * divdt[k1];
+    }
+    if (dump >= 0) {  // test hook (see k_spec_step_vq): divdt, tdt, psdt after the implicit correction
+#pragma unroll
+        for (int k = 0; k < KX; k++) {
+            *(scp(c, t, dump + (long long)(8 + k) * NSP, lane) + e) = divdt[k];
+            *(scp(c, t, dump + (long long)(16 + k) * NSP, lane) + e) = tdt[k];
+        }
+        *(scp(c, t, dump + 24ll * NSP, lane) + e) = psdt;
+        return;
     }
     // ---- D/E. horizontal diffusion, stratospheric drag and time integration (time_stepping.f90:78-144)
     const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
@@ -375,10 +389,11 @@ __global__ void k_update_forcing_params(const Ctx c) {
 void launch_grid_dyn(cudaStream_t s, const Ctx &c, const ScratchLayout &L) {
     k_grid_dyn<<<dim3(NG / 4, c.ntiles), 128, 0, s>>>(c, L);
 }
-void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j1, double dt, double eps, int impl_idx) {
-    k_spec_step_vq<<<dim3(NSPC * 2 * KX / 8, c.ntiles), 256, 0, s>>>(c, L, j1, dt, eps, impl_idx);
-    if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
-    else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx);
+void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j1, double dt, double eps, int impl_idx,
+                      long long dump = -1) {
+    k_spec_step_vq<<<dim3(NSPC * 2 * KX / 8, c.ntiles), 256, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
+    if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
+    else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
 }
 void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part) {
     k_diag_partial<<<dim3(KX * (MX - 1), c.ntiles), 32, 0, s>>>(c, time_lev, part);

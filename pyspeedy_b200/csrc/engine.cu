@@ -485,7 +485,7 @@ static void run_forcing(const Ctx &c, int imode) {
 }
 
 // step(j1, j2, dt) of time_stepping.f90:38-147: tendencies + diffusion + time integration
-static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, int impl_idx) {
+static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, int impl_idx, long long dump = -1) {
     const ScratchLayout &L = E.L;
     const long long tl2 = (long long)(j2 - 1) * NSP * KX;
     // spectral pre-operators: geopotential (time level 1), uvspec, grad(ps)
@@ -502,7 +502,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     prof_mark(E.stream, PC_PHYSICS);
     COUNT(2);
     run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT);
-    launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx);
+    launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx, dump);
     prof_mark(E.stream, PC_SPEC_STEP);
     COUNT(1);
 }
@@ -1017,6 +1017,33 @@ int spdy_debug_raw_step(int64_t h, int j1, int j2, int dt_kind) {
     const double dts[3] = {0.5 * H_DELT, H_DELT, 2.0 * H_DELT};
     run_step_core(c, j1, j2, dts[dt_kind], j1 == 1 ? 0.0 : FL(0.05), dt_kind);
     CK(cudaStreamSynchronize(E.stream));
+    return 0;
+}
+
+// tendencies of one member as returned by get_tendencies(state, ..., j2) (tendencies.f90:11-39): vordt, divdt, tdt
+// (31,32,8) complex each, psdt (31,32), trdt (31,32,8); the prognostic state is not advanced (physics diagnostics
+// are updated exactly as a model step would)
+int spdy_debug_tendencies(int64_t h, int j2, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt) {
+    Member *m = member_of(h);
+    if (!m) return -1;
+    Ctx c = single_ctx(*m);
+    const long long dump = E.L.four;
+    run_step_core(c, 2, j2, 2.0 * H_DELT, FL(0.05), 2, dump);
+    CK(cudaStreamSynchronize(E.stream));
+    auto down = [&](double *dst, long long off, long long n) {
+        for (long long o = 0; o < n; o += (long long)E.stage_elems) {
+            const long long cn = std::min<long long>(E.stage_elems, n - o);
+            k_gather<<<(int)((cn + 255) / 256), 256, 0, E.stream>>>(E.scr, E.L.total, 0, m->lane, off + o, cn, E.d_stage);
+            CK(cudaMemcpyAsync(E.h_stage, E.d_stage, cn * 8, cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            memcpy(dst + o, E.h_stage, cn * 8);
+        }
+    };
+    down(vordt, dump, (long long)NSP * KX);
+    down(divdt, dump + 8ll * NSP, (long long)NSP * KX);
+    down(tdt, dump + 16ll * NSP, (long long)NSP * KX);
+    down(psdt, dump + 24ll * NSP, NSP);
+    down(trdt, dump + 25ll * NSP, (long long)NSP * KX);
     return 0;
 }
 
