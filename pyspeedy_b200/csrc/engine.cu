@@ -98,7 +98,7 @@ struct Engine {
     // arenas
     double *st = nullptr, *sst = nullptr, *scr = nullptr;
     long long st_elems = 0, sst_elems = 0;
-    int cap_tiles = 0, sst_months = 0, scr_tiles = 0, chunk_tiles = 16;
+    int cap_tiles = 0, sst_months = 0, scr_tiles = 0, chunk_tiles = 64;
     long long off[SPDY_NVARS], nelem[SPDY_NVARS], off_tcorh = 0, off_qcorh = 0, off_slots = 0;
     // handles
     std::vector<Member> members;
