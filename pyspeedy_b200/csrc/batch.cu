@@ -118,8 +118,12 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
     Ctx c = ws_ctx(n);
     ws_set_kcos(kcos);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
-    launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
-    launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    if (use_fused_inv()) {
+        launch_spec2grid_fused(E.stream, c, W.d_inv, 1);
+    } else {
+        launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+        launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
+    }
     COUNT(2);
     ws_move(nullptr, grid, WS_GRID, NG, n);
     return 0;
@@ -127,8 +131,12 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
 int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
-    launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
-    launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
+    if (use_fused()) {
+        launch_grid2spec_fused(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
+    } else {
+        launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
+        launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
+    }
     COUNT(2);
     ws_move(nullptr, spec, WS_SPEC, NSP, n);
     return 0;

@@ -426,7 +426,25 @@ __global__ void __launch_bounds__(256) k_ens_sums(const Ctx c, long long off, lo
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
+// SPDY_FUSED selects the fused Legendre+FFT kernels of fused.cu: 0 = none (default), 1 = both directions,
+// 2 = inverse (spec -> grid) only.  See DESIGN.md section 4 for the measurements behind the default.
+static int fused_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("SPDY_FUSED");
+        v = s ? atoi(s) : 0;
+    }
+    return v;
+}
+static bool use_fused() { return fused_mode() == 1; }
+static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
+    if (use_fused_inv()) {  // Legendre + FFT in one kernel, Fourier array stays in shared memory (fused.cu)
+        launch_spec2grid_fused(E.stream, c, d, n);
+        prof_mark(E.stream, PC_FFT_INV);
+        COUNT(1);
+        return;
+    }
     launch_legendre_inv(E.stream, c, d, n, E.L.four);
     prof_mark(E.stream, PC_LEG_INV);
     launch_fft_inv(E.stream, c, d, n, E.L.four);
@@ -434,6 +452,12 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
+    if (use_fused()) {
+        for (int m = 0; m < FM_NMODES; m++)
+            if (counts[m]) launch_grid2spec_fused(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
+        prof_mark(E.stream, PC_FFT_FWD);
+        return;
+    }
     for (int m = 0; m < FM_NMODES; m++)
         if (counts[m]) launch_fft_fwd(E.stream, c, m, lists[m], counts[m], E.L.four), COUNT(1);
     prof_mark(E.stream, PC_FFT_FWD);
@@ -449,8 +473,12 @@ static void run_forward_plain(const Ctx &c, const std::vector<FieldRef> &src, co
     CK(cudaMemcpyAsync(E.d_fwd_tmp, f.data(), f.size() * sizeof(FwdDesc), cudaMemcpyHostToDevice, E.stream));
     CK(cudaMemcpyAsync(E.d_out_tmp, o.data(), o.size() * sizeof(FwdOut), cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    launch_fft_fwd(E.stream, c, mode, E.d_fwd_tmp, (int)f.size(), E.L.four);
-    launch_legendre_dir(E.stream, c, E.d_out_tmp, (int)f.size(), E.L.four);
+    if (use_fused()) {
+        launch_grid2spec_fused(E.stream, c, mode, E.d_fwd_tmp, E.d_out_tmp, (int)f.size());
+    } else {
+        launch_fft_fwd(E.stream, c, mode, E.d_fwd_tmp, (int)f.size(), E.L.four);
+        launch_legendre_dir(E.stream, c, E.d_out_tmp, (int)f.size(), E.L.four);
+    }
     COUNT(2);
     CK(cudaStreamSynchronize(E.stream));
 }
@@ -477,8 +505,12 @@ static void run_forcing(const Ctx &c, int imode) {
         CK(cudaMemcpy(d_f, f, sizeof(f), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_o, o, sizeof(o), cudaMemcpyHostToDevice));
     }
-    launch_fft_fwd(E.stream, c, FM_PLAIN, d_f, 2, L.four);
-    launch_legendre_dir(E.stream, c, d_o, 2, L.four);
+    if (use_fused()) {
+        launch_grid2spec_fused(E.stream, c, FM_PLAIN, d_f, d_o, 2);
+    } else {
+        launch_fft_fwd(E.stream, c, FM_PLAIN, d_f, 2, L.four);
+        launch_legendre_dir(E.stream, c, d_o, 2, L.four);
+    }
     launch_masked_copy(E.stream, c, REF_SCR | L.sfwd, E.off_tcorh, NSP, imode, 1.0);
     launch_masked_copy(E.stream, c, REF_SCR | (L.sfwd + NSP), E.off_qcorh, NSP, imode, 1.0);
     COUNT(4);

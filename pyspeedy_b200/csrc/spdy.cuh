@@ -52,6 +52,7 @@ struct ImplTables {  // depends on the time step (implicit.f90:83-218): three in
 };
 struct GlobTables {
     double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
+    double cpolj[MX * IY * NX]; // [m][j][n]  same values, latitude-major slices for the fused transforms
     double el2[NSPC], elm2[NSPC], trfilt[NSPC], gradym[NSPC], gradyp[NSPC], uvdx[NSPC], uvdym[NSPC], uvdyp[NSPC],
         vddym[NSPC], vddyp[NSPC], dmp[NSPC], dmpd[NSPC], dmps[NSPC];
     double gradx[MX];

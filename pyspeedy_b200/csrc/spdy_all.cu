@@ -1,6 +1,7 @@
 // speedy-b200: unity build of the CUDA library (one translation unit, so the __constant__ tables are shared
 // without relocatable device code).  Build: see pyspeedy_b200/csrc/Makefile.
 #include "transforms.cu"
+#include "fused.cu"
 #include "dynamics.cu"
 #include "physics.cu"
 #include "surface.cu"

@@ -273,6 +273,7 @@ void build_tables(ConstTables &C, GlobTables &G) {
                     double v = P(m, n);
                     if (fabs(v) <= FL(1.e-30)) v = 0.0;
                     G.cpol[(m * NX + n) * IY + j] = v;
+                    G.cpolj[(m * IY + j) * NX + n] = v;
                 }
         }
         // ---- spectral operator tables (spectral.f90:68-110)

@@ -89,3 +89,41 @@ def test_full_size_properties(drv):
     # (4e-3) -- so test determinism instead: same input, same bits
     sa2 = _run(lib, "spdy_batch_grid2spec", ga, (n, NX, MX), dtype=np.complex128)
     assert np.array_equal(sa, sa2)
+
+
+def test_fused_transform_path():
+    """The optional fused Legendre+FFT kernels (csrc/fused.cu, SPDY_FUSED=1) against the oracle, in a fresh process
+    because the switch is read when the library initialises; also 3 model steps through the fused path."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from util import synth_spec, ptr, relerr
+from oracle import oracle as O
+from pyspeedy_b200 import _driver, Speedy, _speedy
+from datetime import datetime
+lib = _driver.lib()
+n = 70
+x = synth_spec(n, seed=21)
+for kcos in (1, 2):
+    g = np.zeros((n, 48, 96)); lib.spdy_batch_spec2grid(ptr(x), ptr(g), kcos, n)
+    assert relerr(g, O.spec2grid(x, kcos)) < 1e-12
+g = O.spec2grid(x, 1)
+s = np.zeros((n, 32, 31), dtype=np.complex128); lib.spdy_batch_grid2spec(ptr(g), ptr(s), n)
+ref = O.grid2spec(g)
+assert relerr(s, ref) < 1e-12 and np.all(s[:, 31, :] == 0) and np.all(s[ref == 0] == 0)
+st = O.State(n_months=1); ctl = O.Control((1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0)); O.load_default_bc(st); assert st.init(ctl) == 0
+m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)); m.set_bc()
+for _ in range(3):
+    assert st.step(ctl) == 0 and _speedy.step(m._state_cnt, m._control_cnt) == 0
+for v in ("vor", "div", "t", "ps", "tr"):
+    assert relerr(m[v], st[v]) < 1e-11, v
+print("fused ok")
+'''
+    env = dict(os.environ, SPDY_FUSED="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
