@@ -97,6 +97,14 @@ __device__ __forceinline__ double *refp(const Ctx &c, int t, FieldRef r, int lan
     return (r & REF_SCR) ? scp(c, t, r & ~REF_SCR, lane) : stp(c, t, r, lane);
 }
 
+// Ampere-style asynchronous 16-byte global -> shared copies (L1 bypass)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // default-REAL literal widened to double, e.g. FL(0.05) == (double)0.05f
 #define FL(x) ((double)(x##f))
 

@@ -23,11 +23,21 @@ namespace spdy {
 
 // ------------------------------------------------------------------------------------------- Legendre inverse
 // One warp = one (field, m-pair); pairs (m, 30-m) balance the triangular truncation: 34 n-terms per pair.
+// What bounds this kernel is the L1/LSU data pipe, not FP64 or HBM (tools/microbench/l1pipe.cu: a warp-uniform
+// value costs 2 SM-cycles through LDG but 1 through LDS; a 256-byte member row costs 2 either way).  The warp
+// therefore copies the Legendre polynomials of its pair (34 rows x 24 latitudes = 6.5 KB, contiguous in cpol)
+// into a private shared-memory slab with cp.async and feeds the FMAs from broadcast LDS.128; the spectral
+// coefficients stream from global memory (read-only path), 6 latitudes x {even,odd} x {re,im} register tile.
+constexpr int LEGI_ROWS = 34;
+constexpr int LEGI_SMEM = 4 * LEGI_ROWS * IY * 8;  // 26,112 bytes per CTA (4 warps)
+__device__ __forceinline__ void leg_stage_rows(double *__restrict__ S, const double *__restrict__ Pm, int nrows, int lane) {
+    const int pieces = nrows * (IY / 2);  // 16-byte pieces, rows are contiguous in cpol[m][n][j]
+    for (int i = lane; i < pieces; i += 32) cp_async16(S + 2 * i, Pm + 2 * i);
+}
 __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, double *__restrict__ F,
-                                              const double *__restrict__ P, const int m0) {
+                                              const double *__restrict__ Ps, const int m0) {
     const int nmax = 31 - m0;  // n0 = 0..nmax are inside the nsh2 mask (legendre.f90:68-77)
     const double *Xr = X + (2 * m0) * TILE, *Xi = Xr + TILE;
-    const double *Pm = P + (size_t)m0 * NX * IY;
 #pragma unroll 1
     for (int jt = 0; jt < 4; jt++) {
         double er[6], ei[6], orr[6], oi[6];
@@ -36,8 +46,8 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
 #pragma unroll 4
         for (int n0 = 0; n0 <= nmax; n0 += 2) {  // even parity: l - m even
             const double xr = __ldg(Xr + (size_t)n0 * M2 * TILE), xi = __ldg(Xi + (size_t)n0 * M2 * TILE);
-            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
-            const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
+            const double2 *p = reinterpret_cast<const double2 *>(Ps + n0 * IY + jt * 6);
+            const double2 p0 = p[0], p1 = p[1], p2 = p[2];
             er[0] += xr * p0.x, ei[0] += xi * p0.x, er[1] += xr * p0.y, ei[1] += xi * p0.y;
             er[2] += xr * p1.x, ei[2] += xi * p1.x, er[3] += xr * p1.y, ei[3] += xi * p1.y;
             er[4] += xr * p2.x, ei[4] += xi * p2.x, er[5] += xr * p2.y, ei[5] += xi * p2.y;
@@ -45,8 +55,8 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
 #pragma unroll 4
         for (int n0 = 1; n0 <= nmax; n0 += 2) {  // odd parity
             const double xr = __ldg(Xr + (size_t)n0 * M2 * TILE), xi = __ldg(Xi + (size_t)n0 * M2 * TILE);
-            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY + jt * 6);
-            const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
+            const double2 *p = reinterpret_cast<const double2 *>(Ps + n0 * IY + jt * 6);
+            const double2 p0 = p[0], p1 = p[1], p2 = p[2];
             orr[0] += xr * p0.x, oi[0] += xi * p0.x, orr[1] += xr * p0.y, oi[1] += xi * p0.y;
             orr[2] += xr * p1.x, oi[2] += xi * p1.x, orr[3] += xr * p1.y, oi[3] += xi * p1.y;
             orr[4] += xr * p2.x, oi[4] += xi * p2.x, orr[5] += xr * p2.y, oi[5] += xi * p2.y;
@@ -62,60 +72,83 @@ __device__ __forceinline__ void leg_inv_one_m(const double *__restrict__ X, doub
 }
 
 __global__ void __launch_bounds__(128) k_legendre_inv(const Ctx c, const InvDesc *__restrict__ descs, long long four_off) {
+    extern __shared__ __align__(16) double leg_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.x >> 2, unit = (blockIdx.x & 3) * 4 + warp;  // 16 units per field
     const int t = blockIdx.y;
     const double *X = refp(c, t, descs[f].src, lane);
     double *F = scp(c, t, four_off + (long long)f * NFOUR, lane);
     const double *P = c.G->cpol;
-    if (unit < 15) {
-        leg_inv_one_m(X, F, P, unit);
-        leg_inv_one_m(X, F, P, 30 - unit);
-    } else {
-        leg_inv_one_m(X, F, P, 15);
-    }
+    double *S = leg_sm + warp * (LEGI_ROWS * IY);
+    const int ma = (unit < 15) ? unit : 15, mb = 30 - unit;
+    double *Sb = S + (32 - ma) * IY;
+    leg_stage_rows(S, P + (size_t)ma * NX * IY, 32 - ma, lane);
+    if (unit < 15) leg_stage_rows(Sb, P + (size_t)mb * NX * IY, 32 - mb, lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    leg_inv_one_m(X, F, S, ma);
+    if (unit < 15) leg_inv_one_m(X, F, Sb, mb);
 }
 
 // -------------------------------------------------------------------------------------------- Legendre direct
+// CTA = the wavenumber pair (m, 30-m) of one field; the two warps of a wavenumber take one parity each (n - m even
+// uses only the N+S fold, odd only the N-S fold), so every Legendre value fetched feeds {re,im} of 32 members.
+// The pair's polynomials are staged in shared memory as above; the 48 Fourier rows of the wavenumber are loaded
+// straight into registers (independent loads, all in flight), folded and weighted (legendre.f90:196-197), then
+// 24-term dot products run two spectral rows (four accumulation chains) at a time (legendre.f90:206-218; rows
+// beyond the nsh2 mask are written as zero).
+constexpr int LEGD_SMEM = LEGI_ROWS * IY * 8;  // 6,528 bytes per CTA
 __global__ void __launch_bounds__(128) k_legendre_dir(const Ctx c, const FwdOut *__restrict__ outs, long long four_off) {
+    __shared__ __align__(16) double Ps[LEGI_ROWS * IY];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x >> 3, m0 = (blockIdx.x & 7) * 4 + warp;  // 32 slots, 31 used
+    const int f = blockIdx.x >> 4, unit = blockIdx.x & 15, sel = warp >> 1, par = warp & 1;
     const int t = blockIdx.y;
-    if (m0 >= MX) return;
-    const double *F = scp(c, t, four_off + (long long)f * NFOUR, lane);
-    double *X = refp(c, t, outs[f].dst, lane);
-    const double *Pm = c.G->cpol + (size_t)m0 * NX * IY;
-    const int nmax = min(30, 31 - m0);  // legendre.f90:206-218: n = 1..trunc+1 under the nsh2 mask
-#pragma unroll 1
-    for (int cc = 0; cc < 2; cc++) {
-        double ev[IY], od[IY];
+    const bool valid = !(unit == 15 && sel == 1);
+    const int ma = (unit < 15) ? unit : 15, mb = 30 - unit;
+    const int m0 = sel ? mb : ma;
+    const double *P = c.G->cpol;
+    // warps 0,1 stage the rows of ma, warps 2,3 those of mb (half of the 16-byte pieces each)
+    if (valid) {
+        const int nrows = 32 - m0, pieces = nrows * (IY / 2);
+        double *S = Ps + (sel ? (32 - ma) * IY : 0);
+        const double *g = P + (size_t)m0 * NX * IY;
+        for (int i = par * 32 + lane; i < pieces; i += 64) cp_async16(S + 2 * i, g + 2 * i);
+    }
+    cp_async_commit();
+    double wr[IY], wi[IY];
+    if (valid) {
+        const double *Fm = scp(c, t, four_off + (long long)f * NFOUR, lane) + (size_t)(2 * m0) * TILE;
 #pragma unroll
-        for (int j = 0; j < IY; j++) {  // legendre.f90:196-197
-            const double fs = F[((size_t)j * M2 + 2 * m0 + cc) * TILE];
-            const double fn = F[((size_t)(IL - 1 - j) * M2 + 2 * m0 + cc) * TILE];
-            ev[j] = (fn + fs) * c_T.wt[j];
-            od[j] = (fn - fs) * c_T.wt[j];
+        for (int j = 0; j < IY; j++) {
+            const double *ps = Fm + (size_t)j * M2 * TILE, *pn = Fm + (size_t)(IL - 1 - j) * M2 * TILE;
+            const double sr = par ? -ps[0] : ps[0], si = par ? -ps[TILE] : ps[TILE];
+            wr[j] = (pn[0] + sr) * c_T.wt[j];
+            wi[j] = (pn[TILE] + si) * c_T.wt[j];
         }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!valid) return;
+    double *X = refp(c, t, outs[f].dst, lane) + (size_t)(2 * m0) * TILE;
+    const double *Pm = Ps + (sel ? (32 - ma) * IY : 0);
+    const int nmax = min(30, 31 - m0);
 #pragma unroll 1
-        for (int n0 = 0; n0 < NX; n0 += 4) {  // n0, n0+2 even parity (ev) ; n0+1, n0+3 odd parity (od): four chains
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const double2 *p = reinterpret_cast<const double2 *>(Pm + n0 * IY);
-            if (n0 <= nmax) {  // rows beyond the mask keep acc = 0 (P is not read: table rows exist up to n = 31)
-                const double w1 = (n0 + 1 <= nmax) ? 1.0 : 0.0, w2 = (n0 + 2 <= nmax) ? 1.0 : 0.0,
-                             w3 = (n0 + 3 <= nmax) ? 1.0 : 0.0;
+    for (int n0 = par; n0 < NX; n0 += 4) {
+        double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+        if (n0 <= nmax) {
+            const bool two = (n0 + 2 <= nmax);  // row n0+2 may lie outside the staged slab: re-use row n0, discard
+            const double2 *p0 = reinterpret_cast<const double2 *>(Pm + n0 * IY), *p1 = two ? p0 + IY : p0;
 #pragma unroll
-                for (int j = 0; j < IY; j += 2) {
-                    const double2 a0 = __ldg(p + (j >> 1)), a1 = __ldg(p + IY / 2 + (j >> 1)),
-                                  a2 = __ldg(p + IY + (j >> 1)), a3 = __ldg(p + 3 * IY / 2 + (j >> 1));
-                    acc[0] += a0.x * ev[j], acc[1] += a1.x * od[j], acc[2] += a2.x * ev[j], acc[3] += a3.x * od[j];
-                    acc[0] += a0.y * ev[j + 1], acc[1] += a1.y * od[j + 1], acc[2] += a2.y * ev[j + 1],
-                        acc[3] += a3.y * od[j + 1];
-                }
-                acc[1] *= w1, acc[2] *= w2, acc[3] *= w3;  // exact: masks are 0 or 1
+            for (int j = 0; j < IY; j += 2) {
+                const double2 a = p0[j >> 1], b = p1[j >> 1];
+                ar0 += a.x * wr[j], ai0 += a.x * wi[j], ar1 += b.x * wr[j], ai1 += b.x * wi[j];
+                ar0 += a.y * wr[j + 1], ai0 += a.y * wi[j + 1], ar1 += b.y * wr[j + 1], ai1 += b.y * wi[j + 1];
             }
-#pragma unroll
-            for (int q = 0; q < 4; q++) X[((size_t)(n0 + q) * M2 + 2 * m0 + cc) * TILE] = acc[q];
+            if (!two) ar1 = 0.0, ai1 = 0.0;
         }
+        double *x0 = X + (size_t)n0 * M2 * TILE, *x1 = x0 + (size_t)2 * M2 * TILE;
+        x0[0] = ar0, x0[TILE] = ai0, x1[0] = ar1, x1[TILE] = ai1;
     }
 }
 
@@ -326,7 +359,8 @@ __global__ void __launch_bounds__(128) k_geopotential(const Ctx c, FieldRef tref
 
 // ------------------------------------------------------------------------------------------------- launchers
 void launch_legendre_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off) {
-    if (nf) k_legendre_inv<<<dim3(nf * 4, c.ntiles), 128, 0, s>>>(c, d, four_off);
+    if (!nf) return;
+    k_legendre_inv<<<dim3(nf * 4, c.ntiles), 128, LEGI_SMEM, s>>>(c, d, four_off);
 }
 void launch_fft_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off) {
     const int nlg = nf * IL;
@@ -345,7 +379,8 @@ void launch_fft_fwd(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, in
     }
 }
 void launch_legendre_dir(cudaStream_t s, const Ctx &c, const FwdOut *o, int nf, long long four_off) {
-    if (nf) k_legendre_dir<<<dim3(nf * 8, c.ntiles), 128, 0, s>>>(c, o, four_off);
+    if (!nf) return;
+    k_legendre_dir<<<dim3(nf * 16, c.ntiles), 128, 0, s>>>(c, o, four_off);
 }
 void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev) {
     k_uvspec<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, vor, dv, u, v, nlev);
