@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     }
     const double ua8 = *(scp(c, t, L.pug8, lane) + e), va8 = *(scp(c, t, L.pvg8, lane) + e);
     const double psa = fast_exp(*(scp(c, t, L.pslg, lane) + e));
-    const double rps = 1.0 / psa;
+    const double rps = fast_rcp(psa);
     double se[KX], rh[KX], qsat[KX];
 #pragma unroll
     for (int k = 0; k < KX; k++) {
@@ -177,22 +177,14 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         }
         if (itop != KX + 1) {
             // entrainment profile (convection.f90:63-72)
-            double entr[KX], sentr = 0.0;
-#pragma unroll
-            for (int k = 1; k < KX - 1; k++) {
-                const double ee = fmax(0.0, c_T.fsg[k] - 0.5);
-                entr[k] = ee * ee;
-                sentr = sentr + entr[k];
-            }
-            sentr = ENTMAX / sentr;
-            const double fm0 = P0 * c_T.dhs[7] / (GRAV * TRCNV * FL(3600.0));
+            const double fm0 = c_T.ph_fm0;  // entrainment profile and fm0: host tables (spdy.cuh)
             const double rdps = 2.0 / (1.0 - PSMIN);
             const double qmax = fmax(FL(1.01) * qa[7], qsat[7]);
             double sb = se[6] + c_T.wvi[6][1] * (se[7] - se[6]);
             double qb = qa[6] + c_T.wvi[6][1] * (qa[7] - qa[6]);
             qb = fmin(qb, qa[7]);
             const double fpsa = psa * fmin(1.0, (psa - PSMIN) * rdps);
-            double fmass = fm0 * fpsa * fmin(5.0, qdif / (qmax - qb));
+            double fmass = fm0 * fpsa * fmin(5.0, qdif * fast_rcp(qmax - qb));
             cbmf = fmass;
             double fus = fmass * se[7], fuq = fmass * qmax, fds = fmass * sb, fdq = fmass * qb;
             dfse[7] = fds - fus;
@@ -203,7 +195,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
                     const int k0 = k - 1, k1 = k - 2;
                     dfse[k0] = fus - fds;
                     dfqa[k0] = fuq - fdq;
-                    const double enmass = (entr[k0] * sentr) * psa * cbmf;
+                    const double enmass = c_T.ph_entrs[k0] * psa * cbmf;
                     fmass = fmass + enmass;
                     fus = fus + enmass * se[k0];
                     fuq = fuq + enmass * qa[k0];
@@ -286,7 +278,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     int icltop_out = 0;
     if (do_sw && act) {  // physics.f90:151-169 ; inactive lanes own no state
         // clouds (shortwave_radiation.f90:325-404)
-        const double gse = (se[6] - se[7]) / (phi[6] - phi[7]);
+        const double gse = (se[6] - se[7]) * fast_rcp(phi[6] - phi[7]);
         double cloudc;
         int icltop;
         if (rh[6] > RHCL1) cloudc = rh[6] - RHCL1, icltop = KX - 1;
@@ -396,7 +388,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
             tau2[(k + KX * 2) * lev] = t3, tau2[(k + KX * 3) * lev] = t4;
             ttrsw[k * lev] = trsw[k] * rps * c_T.grdscp[k];  // physics.f90:166-168
         }
-        const double eps1 = EPSLW / (c_T.dhs[0] + c_T.dhs[1]);
+        const double eps1 = c_T.ph_eps1;
         strat[0] = *ST2D(V_stratospheric_correction) * psa;
         strat[lev] = eps1 * psa;
     }
@@ -405,17 +397,14 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     //      evaluated here so that se/rh/qsat/phi die before the long-wave sweeps (register pressure)
     double tv[KX], qv[KX];
     {
-        const double trshc = FL(6.0), trvdi = FL(24.0), trvds = FL(6.0), redshc = FL(0.5), rhgrad = FL(0.5), segrad = FL(0.1);
-        const double cshc = c_T.dhs[7] / FL(3600.0);
-        const double cvdi = (c_T.sigh[7] - c_T.sigh[1]) / (double)(6.0f * 3600.0f);
-        const double fshcq = cshc / trshc, fshcse = cshc / (trshc * CP);
-        const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * CP);
+        const double redshc = FL(0.5), segrad = FL(0.1);
+        const double fshcq = c_T.ph_fshcq, fshcse = c_T.ph_fshcse, fvdise = c_T.ph_fvdise;  // host tables
 #pragma unroll
         for (int k = 0; k < KX; k++) tv[k] = 0.0, qv[k] = 0.0;
-        const double rsig6 = 1.0 / c_T.dhs[6], rsig7 = 1.0 / c_T.dhs[7];
+        const double rsig6 = c_T.ph_rdhs[6], rsig7 = c_T.ph_rdhs[7];
         {
-            const double drh0 = rhgrad * (c_T.fsg[7] - c_T.fsg[6]);
-            const double fvdiq2 = fvdiq * c_T.sigh[7];
+            const double drh0 = c_T.ph_drh0[7];
+            const double fvdiq2 = c_T.ph_fvdiq2[7];
             const double dmse = se[7] - se[6] + ALHC * (qa[7] - qsat[6]);
             const double drh = rh[7] - rh[6];
             double fcnv = 1.0;
@@ -438,13 +427,13 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
 #pragma unroll
         for (int k = 3; k <= KX - 2; k++)  // 1-based k
             if (c_T.sigh[k] > 0.5) {
-                const double drh0 = rhgrad * (c_T.fsg[k] - c_T.fsg[k - 1]);
-                const double fvdiq2 = fvdiq * c_T.sigh[k];
+                const double drh0 = c_T.ph_drh0[k];
+                const double fvdiq2 = c_T.ph_fvdiq2[k];
                 const double drh = rh[k] - rh[k - 1];
                 if (drh >= drh0) {
                     const double fluxq = fvdiq2 * qsat[k - 1] * drh;
-                    qv[k - 1] = qv[k - 1] + fluxq * (1.0 / c_T.dhs[k - 1]);
-                    qv[k] = qv[k] - fluxq * (1.0 / c_T.dhs[k]);
+                    qv[k - 1] = qv[k - 1] + fluxq * c_T.ph_rdhs[k - 1];
+                    qv[k] = qv[k] - fluxq * c_T.ph_rdhs[k];
                 }
             }
 #pragma unroll
@@ -452,8 +441,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
             const double se0 = se[k + 1] + segrad * (phi[k] - phi[k + 1]);
             if (se[k] < se0) {
                 const double fluxse = fvdise * (se0 - se[k]);
-                tv[k] = tv[k] + fluxse * (1.0 / c_T.dhs[k]);
-                const double r1 = 1.0 / (1.0 - c_T.sigh[k + 1]);
+                tv[k] = tv[k] + fluxse * c_T.ph_rdhs[k];
+                const double r1 = c_T.ph_r1sig[k];
 #pragma unroll
                 for (int k1 = k + 1; k1 < KX; k1++) tv[k1] = tv[k1] - fluxse * r1;
             }
@@ -532,7 +521,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         const double gtemp0 = 1.0 - FTEMP0, rcp = 1.0 / CP;
         const double dt1 = c_T.wvi[KX - 1][1] * (ta7 - ta6);
         double t1l = ta7 + dt1;
-        double t1s = t1l - phi0 * dt1 / (RGAS * FL(288.0) * c_T.sigl[KX - 1]);
+        double t1s = t1l - phi0 * dt1 * c_T.ph_rt1s;
         const double t2s = ta7 + rcp * phi7;
         const double t2l = t2s - rcp * phi0;
         if (ta7 > ta6) {
@@ -542,8 +531,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
             t1l = ta7, t1s = ta7;
         }
         const double t0 = t1s + fmask * (t1l - t1s);
-        const double denvvs0 = (P0 * psa / (RGAS * t0)) * sqrt(u0 * u0 + v0 * v0 + VGUST * VGUST);
-        double tskin = land_temp + CTDAY * sqrt(c_T.coa[j]) * ssrd * (1.0 - alb_land) * psa;
+        const double denvvs0 = (P0 * psa * fast_rcp(RGAS * t0)) * sqrt(u0 * u0 + v0 * v0 + VGUST * VGUST);
+        double tskin = land_temp + CTDAY * c_T.ph_sqcoa[j] * ssrd * (1.0 - alb_land) * psa;
         const double rdth = FSTAB / DTHETA, astab = 0.5;
         const double dthl = (tskin > t2l) ? fmin(DTHETA, tskin - t2l) : fmax(-DTHETA, astab * (tskin - t2l));
         const double denvvs1 = denvvs0 * (1.0 + dthl * rdth);
@@ -562,7 +551,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         hfl1 = hfl1 - clamb * (tskin - land_temp);
         double qsat02 = qsat_of(tskin + 1.0, psa, 1.0);
         qsat02 = (evap1 > 0.0) ? saw * (qsat02 - qsat01) : 0.0;
-        const double dtskin = hfl1 / (clamb + dslr + CHL * denvvs1 * (CP + ALHC * qsat02));
+        const double dtskin = hfl1 * fast_rcp(clamb + dslr + CHL * denvvs1 * (CP + ALHC * qsat02));
         tskin = tskin + dtskin;
         shf1 = shf1 + chlcp * denvvs1 * dtskin;
         evap1 = evap1 + CHL * denvvs1 * qsat02 * dtskin;

@@ -41,6 +41,15 @@ struct ConstTables {
     // semi-implicit matrices for the regular leapfrog step (dt = 2*delt): constant-bank operands of the 8x8
     // mat-vecs in k_spec_step_dt (implicit.f90:234-289)
     double xc2[KX * KX], xd2[KX * KX], xj2[KX * KX * 64], dhsx2[KX];
+    // column-physics constants that the reference re-derives on every call from the sigma-level tables
+    // (convection.f90:63-72,84 ; vertical_diffusion.f90:62-76 ; shortwave_radiation.f90:205 ; surface_fluxes.f90:118,175)
+    double ph_entrs[KX];   // entr(k) * (entmax / sum(entr))
+    double ph_rdhs[KX];    // 1 / dhs(k)
+    double ph_r1sig[KX];   // 1 / (1 - sigh(k+1)), k = 0..kx-2
+    double ph_drh0[KX];    // rhgrad * (fsg(k) - fsg(k-1)), 0-based k >= 1
+    double ph_fvdiq2[KX];  // fvdiq * sigh(k)
+    double ph_sqcoa[IL];   // sqrt(coa(j))
+    double ph_fm0, ph_eps1, ph_fshcq, ph_fshcse, ph_fvdiq, ph_fvdise, ph_rt1s;
 };
 
 // ---- larger tables in global memory (warp-uniform loads) ---------------------------------------------------

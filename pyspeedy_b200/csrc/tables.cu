@@ -201,6 +201,32 @@ void build_tables(ConstTables &C, GlobTables &G) {
     }
     C.wvi[KX - 1][0] = 0.0;
     C.wvi[KX - 1][1] = (F_LOG099 - C.sigl[KX - 1]) * C.wvi[KX - 2][0];
+    // ---- column-physics constants (same operation order as the reference's per-call evaluation)
+    {
+        const double ENTMAX = FL(0.5), TRCNV = FL(6.0), EPSLW = FL(0.05);
+        double entr[KX] = {0}, sentr = 0.0;
+        for (int k = 1; k < KX - 1; k++) {
+            const double ee = fmax(0.0, C.fsg[k] - 0.5);
+            entr[k] = ee * ee;
+            sentr = sentr + entr[k];
+        }
+        sentr = ENTMAX / sentr;
+        for (int k = 0; k < KX; k++) C.ph_entrs[k] = entr[k] * sentr;
+        C.ph_fm0 = H_P0 * C.dhs[7] / (H_GRAV * TRCNV * FL(3600.0));
+        C.ph_eps1 = EPSLW / (C.dhs[0] + C.dhs[1]);
+        const double trshc = FL(6.0), trvdi = FL(24.0), trvds = FL(6.0), rhgrad = FL(0.5);
+        const double cshc = C.dhs[7] / FL(3600.0);
+        const double cvdi = (C.sigh[7] - C.sigh[1]) / (double)(6.0f * 3600.0f);
+        C.ph_fshcq = cshc / trshc, C.ph_fshcse = cshc / (trshc * H_CP);
+        C.ph_fvdiq = cvdi / trvdi, C.ph_fvdise = cvdi / (trvds * H_CP);
+        for (int k = 0; k < KX; k++) {
+            C.ph_rdhs[k] = 1.0 / C.dhs[k];
+            C.ph_fvdiq2[k] = C.ph_fvdiq * C.sigh[k];
+            if (k >= 1) C.ph_drh0[k] = rhgrad * (C.fsg[k] - C.fsg[k - 1]);
+            if (k < KX - 1) C.ph_r1sig[k] = 1.0 / (1.0 - C.sigh[k + 1]);
+        }
+        C.ph_rt1s = 1.0 / (H_RGAS * FL(288.0) * C.sigl[KX - 1]);
+    }
     // ---- latitudes (geometry.f90:107-131): REAL(4) argument and cosf
     double sia_half[IY], coa_half[IY];
     for (int j = 0; j < IY; j++) {
@@ -213,6 +239,7 @@ void build_tables(ConstTables &C, GlobTables &G) {
         C.radang[j] = -asin(sia_half[j]), C.radang[jn] = asin(sia_half[j]);
         C.cosgr[j] = C.cosgr[jn] = 1.0 / coa_half[j];
         C.cosgr2[j] = C.cosgr2[jn] = 1.0 / (coa_half[j] * coa_half[j]);
+        C.ph_sqcoa[j] = C.ph_sqcoa[jn] = sqrt(coa_half[j]);
     }
     for (int j = 0; j < IL; j++) C.coriol[j] = 2.0 * H_OMEGA * C.sia[j];
     // ---- FFT twiddles (fftpack.f90:39-66) for the factor sequence 2,4,4,3
