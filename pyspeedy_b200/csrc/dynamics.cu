@@ -333,10 +333,16 @@ __global__ void __launch_bounds__(32) k_diag_final(const Ctx c, const int time_l
 
 // --------------------------------------------------------------------------------------------- member control
 // speedy.f90:41-53: per-member flags for this step
+__device__ __forceinline__ double date_code(const Ctx &c, int t, int lane) {
+    return (slot(c, t, lane, SL_YEAR) * 16.0 + slot(c, t, lane, SL_MONTH)) * 32.0 + slot(c, t, lane, SL_DAY);
+}
 __global__ void k_control_pre(const Ctx c) {
     const int lane = threadIdx.x, t = blockIdx.x;
     if (!lane_active(c, t, lane)) return;
     const int step = (int)slot(c, t, lane, SL_STEP);
+    // coupler climatology cache: valid for the current date unless the host touched the member since the last step
+    slot(c, t, lane, SL_CPLSTAMP) = (slot(c, t, lane, SL_CPLDIRTY) != 0.0) ? -1.0 : date_code(c, t, lane);
+    slot(c, t, lane, SL_CPLDIRTY) = 0.0;
     slot(c, t, lane, SL_ERR) = 0.0;
     slot(c, t, lane, SL_DAILY) = (step % NSTEPS == 0) ? 1.0 : 0.0;
     slot(c, t, lane, SL_SW) = (step % NSTRAD == 0) ? 1.0 : 0.0;

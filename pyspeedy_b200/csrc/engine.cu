@@ -555,6 +555,7 @@ static void run_model_step(const Ctx &c, bool any_daily) {
     COUNT(4);
 }
 
+static void set_slot_host(const Member &m, int s, double v);
 static void upload_control(Member &m, Control &ctl) {
     // model_control.f90:73-110,166-186 evaluated on the host for the upload; the device then advances its copy
     static const int dim[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
@@ -567,6 +568,7 @@ static void upload_control(Member &m, Control &ctl) {
     CK(cudaMemcpyAsync(E.d_stage, v, sizeof(v), cudaMemcpyHostToDevice, E.stream));
     k_scatter<<<1, 32, 0, E.stream>>>(E.st, E.st_elems, m.tile, m.lane, E.off_slots + SL_STEP, 10, E.d_stage);
     CK(cudaStreamSynchronize(E.stream));
+    set_slot_host(m, SL_CPLDIRTY, 1.0);
 }
 static void advance_host_date(Control &c) {  // model_control.f90:113-163
     static const int dim[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
@@ -1015,6 +1017,7 @@ int spdy_set(int64_t h, int v, const void *src, size_t bytes) {
         }
         if (v == V_current_step) m->current_step = (int)x;
         set_slot_host(*m, scalar_slot(v), x);
+        set_slot_host(*m, SL_CPLDIRTY, 1.0);
         return 0;
     }
     if (d.kind == SPDY_F4) {
@@ -1026,6 +1029,7 @@ int spdy_set(int64_t h, int v, const void *src, size_t bytes) {
     }
     if (bytes != (size_t)var_elems(*m, v) * 8) return -2;
     if (bytes) xfer_array(*m, v, (double *)src, true);
+    set_slot_host(*m, SL_CPLDIRTY, 1.0);  // the coupler re-derives its interpolated climatology on the next step
     return 0;
 }
 

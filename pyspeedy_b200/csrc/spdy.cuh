@@ -26,6 +26,7 @@ constexpr int NSTEPS = 36, NSTRAD = 3;
 enum Slot {
     SL_STEP = 0, SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE, SL_MONTH_IDX, SL_IMONT1, SL_TMONTH, SL_TYEAR,
     SL_CO2, SL_CO2REF, SL_INCCO2, SL_SW, SL_LANDCPL, SL_SSTACPL, SL_ERR, SL_NMONTHS, SL_INITIALIZED, SL_DAILY,
+    SL_CPLSTAMP, SL_CPLDIRTY,  // coupler climatology cache (surface.cu: k_couple)
     SL_COUNT = 32
 };
 

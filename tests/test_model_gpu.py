@@ -161,3 +161,37 @@ def test_grid_spectral_services(oracle):
     m.grid_filter()
     for v in ["u_grid", "t_grid", "q_grid", "ps_grid"]:
         assert relerr(m[v], st[v]) < 1e-10, v
+
+
+SURF = ["land_temp", "sst_am", "stl_lm", "tice_om", "sst_om", "sice_om", "stlcl_obs", "snowdcl_obs", "soilwcl_obs",
+        "sstcl_ob", "sicecl_ob", "ticecl_ob", "snow_depth", "soil_avail_water", "sice_am", "tice_am", "ssti_om",
+        "sstan_am", "hfluxn"]
+
+
+def test_coupler_across_day_boundary_and_host_writes(oracle):
+    """The coupler re-uses its interpolated climatology within a day (surface.cu: k_couple).  Across the day
+    boundary and after a host write to a boundary field the results must still follow the reference, which
+    re-interpolates on every step (speedy.f90:72, sea_model.f90:193-260)."""
+    from pyspeedy_b200 import Speedy, _speedy
+
+    st, ctl = oracle_member(oracle, end=(1982, 1, 3, 0, 0))
+    m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 3))
+    m.set_bc()
+    for step in range(40):
+        assert st.step(ctl) == 0
+        assert _speedy.step(m._state_cnt, m._control_cnt) == 0
+        if step in (0, 1, 34, 35, 36, 37, 39):
+            for v in SURF:
+                assert relerr(m[v], st[v]) < 1e-8, (step, v, relerr(m[v], st[v]))
+    # host write in the middle of a day: visible to the very next step on both sides
+    sst12 = st["sst12"].copy()
+    sst12 += 1.5
+    st["sst12"] = sst12
+    m["sst12"] = sst12
+    before = m["sstcl_ob"].copy()
+    for step in range(2):
+        assert st.step(ctl) == 0
+        assert _speedy.step(m._state_cnt, m._control_cnt) == 0
+        for v in SURF:
+            assert relerr(m[v], st[v]) < 1e-8, ("after write", step, v, relerr(m[v], st[v]))
+    assert np.abs(m["sstcl_ob"] - before).max() > 0.5
