@@ -129,10 +129,10 @@ __device__ __forceinline__ void vdspec_comp(const double gx, const double ym, co
 }
 
 // leapfrog + Robert-Asselin-Williams filter on one component (time_stepping.f90:164-188)
-__device__ __forceinline__ void raw_update(double *p1, double *p2, double fdt, const double trf, const int j1,
-                                           const double dt, const double eps, const bool act) {
+// (o1, o2 = current values of the two time levels, loaded by the caller so that loads can be batched)
+__device__ __forceinline__ void raw_update(double *p1, double *p2, double o1, double o2, double fdt, const double trf,
+                                           const int j1, const double dt, const double eps, const bool act) {
     fdt = fdt * trf;  // truncate (ix == 4*iy)
-    double o1 = *p1, o2 = *p2;
     const double fnew = o1 + dt * fdt;
     double oj1 = (j1 == 1) ? o1 : o2;
     o1 = oj1 + (D_WIL * eps) * ((o1 - 2.0 * oj1) + fnew);
@@ -166,15 +166,15 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
         *(scp(c, t, dump + (long long)(25 + k) * NSP, lane) + e) = trdt;
         return;
     }
-    const double v1 = *vor, q1 = *trs;
+    const double v1 = *vor, q1 = *trs, v2 = vor[tl], q2 = trs[tl];
     const double dmp = G->dmp[q], dmpd = G->dmpd[q], dmps = G->dmps[q];
     double vordt = (vo - dmp * v1) * I->dmp1[q];
     if (k == 0 && m == 0) vordt = vordt - (1.0 / ((double)(24.0f * 30.0f) * FL(3600.0))) * v1;
     vordt = (vordt - dmps * v1) * I->dmp1s[q];
     const double ctq = q1 + *(stp(c, t, c.off_qcorh, lane) + e) * c_T.qcorv[k];
     trdt = (trdt - dmpd * ctq) * I->dmp1d[q];
-    raw_update(vor, vor + tl, vordt, trf, j1, dt, eps, act);
-    raw_update(trs, trs + tl, trdt, trf, j1, dt, eps, act);
+    raw_update(vor, vor + tl, v1, v2, vordt, trf, j1, dt, eps, act);
+    raw_update(trs, trs + tl, q1, q2, trdt, trf, j1, dt, eps, act);
 }
 
 // Divergence, temperature, log(ps): coupled in the vertical by the semi-implicit scheme -> one thread per
@@ -196,6 +196,15 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
     const double *phi = stp(c, t, c.off[V_phi], lane) + e;
     const double el2 = G->el2[q], trf = G->trfilt[q];
     const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q];
+    // rows needed only after the (long) implicit solve: start pulling them into L2 now
+    if (dump < 0) {
+#pragma unroll
+        for (int k = 0; k < KX; k++) {
+            prefetch_l2(phi + k * lev), prefetch_l2(tt + k * lev);
+            prefetch_l2(dvs + tl + k * lev), prefetch_l2(tt + tl + k * lev);
+        }
+        prefetch_l2(ps), prefetch_l2(ps + lev), prefetch_l2(stp(c, t, c.off_tcorh, lane) + e);
+    }
 
     double divdt[KX], tdt[KX], d1[KX];
     // ---- A. grid-point tendencies in spectral space (tendencies.f90:238-268)
@@ -278,18 +287,22 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
     const double dmp1 = I->dmp1[q], dmp1d = I->dmp1d[q], dmp1s = I->dmp1s[q];
     const double sdrag = 1.0 / ((double)(24.0f * 30.0f) * FL(3600.0));
     const double tcorh = *(stp(c, t, c.off_tcorh, lane) + e);
-    raw_update(ps, ps + lev, psdt, trf, j1, dt, eps, act);
+    // all read-modify-write operands are loaded before the first store (loads behind a store would serialise)
+    double t1[KX], t2[KX], d2[KX];
+#pragma unroll
+    for (int k = 0; k < KX; k++) t1[k] = tt[k * lev], t2[k] = tt[tl + k * lev], d2[k] = dvs[tl + k * lev];
+    const double ps2 = ps[lev];
+    raw_update(ps, ps + lev, ps1, ps2, psdt, trf, j1, dt, eps, act);
 #pragma unroll
     for (int k = 0; k < KX; k++) {
-        const double t1 = tt[k * lev];
         double dd = (divdt[k] - dmpd * d1[k]) * dmp1d;
-        const double ctmp = t1 + tcorh * c_T.tcorv[k];
+        const double ctmp = t1[k] + tcorh * c_T.tcorv[k];
         double td = (tdt[k] - dmp * ctmp) * dmp1;
         if (k == 0 && m == 0) dd = dd - sdrag * d1[k];
         dd = (dd - dmps * d1[k]) * dmp1s;
         td = (td - dmps * ctmp) * dmp1s;
-        raw_update(dvs + k * lev, dvs + tl + k * lev, dd, trf, j1, dt, eps, act);
-        raw_update(tt + k * lev, tt + tl + k * lev, td, trf, j1, dt, eps, act);
+        raw_update(dvs + k * lev, dvs + tl + k * lev, d1[k], d2[k], dd, trf, j1, dt, eps, act);
+        raw_update(tt + k * lev, tt + tl + k * lev, t1[k], t2[k], td, trf, j1, dt, eps, act);
     }
 }
 
@@ -314,21 +327,36 @@ __global__ void __launch_bounds__(32) k_diag_partial(const Ctx c, const int time
     double *p = scp(c, t, part + 2 * (k * (MX - 1) + (m - 1)), lane);
     p[0] = d1, p[TILE] = d2;
 }
-__global__ void __launch_bounds__(32) k_diag_final(const Ctx c, const int time_lev, const long long part) {
-    const int lane = threadIdx.x, t = blockIdx.x;
+// Second stage + the member bookkeeping that follows the check in do_single_step (speedy.f90:59-69).  One CTA per
+// tile, warp k sums level k: its 30 partial pairs are loaded together and added in the serial order m = 1..30.
+// mode 0: check only (initialisation).  mode 1: step counter + 1 before the check, calendar advance after it for
+// the members that passed (model_control.f90:113-163).
+__device__ __forceinline__ void advance_calendar(const Ctx &c, int t, int lane);
+__global__ void __launch_bounds__(256) k_diag_final(const Ctx c, const int time_lev, const long long part, const int mode) {
+    __shared__ int s_bad[KX][TILE];
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5, t = blockIdx.x;
     const size_t lev = (size_t)NSP * TILE, tl = (size_t)KX * lev * (time_lev - 1);
     const double *tt = stp(c, t, c.off[V_t], lane) + tl;
-    bool bad = false;
-    for (int k = 0; k < KX; k++) {
-        double d1 = 0.0, d2 = 0.0;
-        for (int m = 0; m < MX - 1; m++) {
-            const double *p = scp(c, t, part + 2 * (k * (MX - 1) + m), lane);
-            d1 += p[0], d2 += p[TILE];
-        }
-        const double d3 = 0x1.6a09e6p-1 * tt[k * lev];  // sqrt(0.5) REAL(4)
-        bad = bad || (d1 > 500.0 || d2 > 500.0 || d3 < 180.0 || d3 > 320.0);
+    double p1[MX - 1], p2[MX - 1];
+#pragma unroll
+    for (int m = 0; m < MX - 1; m++) {
+        const double *p = scp(c, t, part + 2 * (k * (MX - 1) + m), lane);
+        p1[m] = p[0], p2[m] = p[TILE];
     }
-    if (bad && lane_active(c, t, lane)) slot(c, t, lane, SL_ERR) = -2.0;
+    const double t00 = tt[k * lev];
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < MX - 1; m++) d1 += p1[m], d2 += p2[m];
+    const double d3 = 0x1.6a09e6p-1 * t00;  // sqrt(0.5) REAL(4)
+    s_bad[k][lane] = (d1 > 500.0 || d2 > 500.0 || d3 < 180.0 || d3 > 320.0) ? 1 : 0;
+    __syncthreads();
+    if (k != 0 || !lane_active(c, t, lane)) return;
+    int bad = 0;
+#pragma unroll
+    for (int kk = 0; kk < KX; kk++) bad |= s_bad[kk][lane];
+    if (mode == 1) slot(c, t, lane, SL_STEP) = slot(c, t, lane, SL_STEP) + 1.0;
+    if (bad) slot(c, t, lane, SL_ERR) = -2.0;
+    if (mode == 1 && !bad && slot(c, t, lane, SL_ERR) == 0.0) advance_calendar(c, t, lane);
 }
 
 // --------------------------------------------------------------------------------------------- member control
@@ -362,10 +390,7 @@ __device__ __forceinline__ void update_forcing_params(const Ctx &c, int t, int l
     slot(c, t, lane, SL_TYEAR) = (double)(((float)(cum + day) - 0.5f) / 365.0f);
 }
 // speedy.f90:59-69 + model_control.f90:113-163: step counter, then (if the check passed) the calendar
-__global__ void k_control_post(const Ctx c) {
-    const int lane = threadIdx.x, t = blockIdx.x;
-    if (!lane_active(c, t, lane)) return;
-    if (slot(c, t, lane, SL_ERR) != 0.0) return;
+__device__ __forceinline__ void advance_calendar(const Ctx &c, int t, int lane) {
     int year = (int)slot(c, t, lane, SL_YEAR), month = (int)slot(c, t, lane, SL_MONTH),
         day = (int)slot(c, t, lane, SL_DAY), hour = (int)slot(c, t, lane, SL_HOUR),
         minute = (int)slot(c, t, lane, SL_MINUTE), midx = (int)slot(c, t, lane, SL_MONTH_IDX);
@@ -382,11 +407,6 @@ __global__ void k_control_post(const Ctx c) {
     slot(c, t, lane, SL_HOUR) = hour, slot(c, t, lane, SL_MINUTE) = minute, slot(c, t, lane, SL_MONTH_IDX) = midx;
     update_forcing_params(c, t, lane);
 }
-__global__ void k_step_increment(const Ctx c) {
-    const int lane = threadIdx.x, t = blockIdx.x;
-    if (!lane_active(c, t, lane)) return;
-    slot(c, t, lane, SL_STEP) = slot(c, t, lane, SL_STEP) + 1.0;
-}
 __global__ void k_update_forcing_params(const Ctx c) {
     const int lane = threadIdx.x, t = blockIdx.x;
     if (lane_active(c, t, lane)) update_forcing_params(c, t, lane);
@@ -401,13 +421,11 @@ void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int 
     if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
     else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
 }
-void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part) {
+void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part, int mode) {
     k_diag_partial<<<dim3(KX * (MX - 1), c.ntiles), 32, 0, s>>>(c, time_lev, part);
-    k_diag_final<<<c.ntiles, 32, 0, s>>>(c, time_lev, part);
+    k_diag_final<<<c.ntiles, 256, 0, s>>>(c, time_lev, part, mode);
 }
 void launch_control_pre(cudaStream_t s, const Ctx &c) { k_control_pre<<<c.ntiles, 32, 0, s>>>(c); }
-void launch_control_post(cudaStream_t s, const Ctx &c) { k_control_post<<<c.ntiles, 32, 0, s>>>(c); }
-void launch_step_increment(cudaStream_t s, const Ctx &c) { k_step_increment<<<c.ntiles, 32, 0, s>>>(c); }
 void launch_update_forcing_params(cudaStream_t s, const Ctx &c) { k_update_forcing_params<<<c.ntiles, 32, 0, s>>>(c); }
 
 }  // namespace spdy

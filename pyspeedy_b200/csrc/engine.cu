@@ -547,12 +547,10 @@ static void run_model_step(const Ctx &c, bool any_daily) {
     if (any_daily) run_forcing(c, 1);
     prof_mark(E.stream, PC_FORCING);
     run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2);
-    launch_step_increment(E.stream, c);
-    launch_diag(E.stream, c, 2, E.L.diagp);
-    launch_control_post(E.stream, c);
+    launch_diag(E.stream, c, 2, E.L.diagp, 1);  // step counter, check_diagnostics, calendar
     launch_couple(E.stream, c, 0);
     prof_mark(E.stream, PC_POST);
-    COUNT(4);
+    COUNT(3);
 }
 
 static void set_slot_host(const Member &m, int s, double v);
@@ -699,7 +697,7 @@ static int init_member(Member &m, Control &ctl) {
     run_forward_plain(c, {REF_SCR | L.px}, {REF_SCR | L.dpy});
     launch_init_spec(E.stream, c, REF_SCR | L.dpx, REF_SCR | L.dpy);
     k_set_slot<<<1, 32, 0, E.stream>>>(c, SL_ERR, 0.0);
-    launch_diag(E.stream, c, 1, E.L.diagp);
+    launch_diag(E.stream, c, 1, E.L.diagp, 0);
     COUNT(3);
     const int err = (int)get_slot_host(m, SL_ERR);
     if (err != 0) return err;
@@ -947,7 +945,7 @@ int spdy_check(int64_t h) {
     if (!m) return -1;
     Ctx c = single_ctx(*m);
     k_set_slot<<<1, 32, 0, E.stream>>>(c, SL_ERR, 0.0);
-    launch_diag(E.stream, c, 1, E.L.diagp);
+    launch_diag(E.stream, c, 1, E.L.diagp, 0);
     COUNT(2);
     return (int)get_slot_host(*m, SL_ERR);
 }

@@ -70,7 +70,6 @@ __device__ __forceinline__ double qsat_of(double ta, double ps, double sig) {
     const double q = e0 * fast_exp(cc * (ta - t0) * fast_rcp(ta - tt));
     return FL(622.0) * q * fast_rcp(sig * ps - FL(0.378) * q);
 }
-__device__ __forceinline__ void prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // x**3.0 and x**4.0 of longwave_radiation.f90:61,67 and surface_fluxes.f90:216,296: the reference calls the libm
 // power function; the products below differ from it by at most 2 ulp (2e-16 relative), far inside the 1e-12 parity
 // tolerance, and cost 2 multiplies instead of ~150 instructions each.
