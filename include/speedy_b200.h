@@ -57,6 +57,9 @@ int spdy_synchronize(void);
 /* elapsed device time (ms) of the last spdy_run_steps / spdy_parallel_step call, CUDA events on the launch stream */
 float spdy_last_elapsed_ms(void);
 long long spdy_kernel_launches(void);       /* kernels launched by this library so far */
+/* The member's model date as the device calendar holds it (control_params%model_datetime of the bound control,
+   model_control.f90:113-163); out = {year, month, day, hour, minute}.  Returns 0, or -1 for an unknown handle. */
+int spdy_get_model_datetime(int64_t state, int *out);
 /* partial sums for ensemble mean / spread of a grid variable over the listed members:
  * sum[i] = sum_m x_m[i], sumsq[i] = sum_m (x_m[i]-shift[i])^2, both device-resident results copied to host */
 int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const double *shift, double *sum, double *sumsq);

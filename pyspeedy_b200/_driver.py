@@ -42,6 +42,8 @@ def lib():
         L.spdy_create_datetime.restype = i64
         L.spdy_create_datetime.argtypes = [ci] * 5
         L.spdy_get_datetime.argtypes = [i64, vp]
+        L.spdy_get_model_datetime.argtypes = [i64, vp]
+        L.spdy_get_model_datetime.restype = ci
         L.spdy_close_datetime.argtypes = [i64]
         L.spdy_controlparams_init.restype = i64
         L.spdy_controlparams_init.argtypes = [i64, i64]
@@ -112,6 +114,14 @@ class _SpeedyDriver:
     def get_datetime(container):
         out = np.zeros(5, dtype=np.int32)
         lib().spdy_get_datetime(int(container), _ptr(out))
+        return tuple(int(x) for x in out)
+
+    @staticmethod
+    def get_model_datetime(state_cnt):
+        """Extension: the member's date on the device calendar."""
+        out = np.zeros(5, dtype=np.int32)
+        if lib().spdy_get_model_datetime(int(state_cnt), _ptr(out)) != 0:
+            raise ValueError("unknown state container")
         return tuple(int(x) for x in out)
 
     @staticmethod

@@ -847,6 +847,14 @@ int spdy_synchronize(void) {
 float spdy_last_elapsed_ms(void) { return E.last_ms; }
 long long spdy_kernel_launches(void) { return g_launches; }
 
+int spdy_get_model_datetime(int64_t h, int *out) {
+    Member *m = member_of(h);
+    if (!m) return -1;
+    const int s[5] = {SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE};
+    for (int i = 0; i < 5; i++) out[i] = (int)get_slot_host(*m, s[i]);
+    return 0;
+}
+
 int spdy_reserve(int n_members) {
     engine_init();
     ensure_state_tiles((n_members + TILE - 1) / TILE);

@@ -1,0 +1,112 @@
+"""Edge cases of the ensemble driver that the reference's API allows (speedy_driver.f90.j2:58-79 takes any list of
+state/control containers): members of one 32-member tile at different dates (year end, leap day, mid-year month
+interpolation), ragged ensembles, a failing member next to healthy ones."""
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+
+PROG = ["vor", "div", "t", "ps", "tr"]
+SURF = ["land_temp", "sst_am", "stl_lm", "tice_om", "sst_om", "snow_depth", "soil_avail_water", "alb_surface",
+        "flux_solar_in", "tsr", "olr", "precnv", "hfluxn"]
+
+
+def _oracle_member(O, start, end):
+    st = O.State(n_months=1)
+    ctl = O.Control(start, end)
+    O.load_default_bc(st)
+    assert st.init(ctl) == 0
+    return st, ctl
+
+
+def test_members_of_one_tile_at_different_dates(oracle):
+    """Calendar, daily forcing, short-wave phase and coupler cache are per member: three members that share a tile
+    run through a year end, a leap day and a July day in one parallel_step call sequence."""
+    from pyspeedy_b200 import Speedy, _speedy
+
+    periods = [((1983, 12, 31, 0, 0), (1984, 1, 2, 0, 0)),
+               ((1984, 2, 28, 0, 0), (1984, 3, 1, 0, 0)),
+               ((1982, 7, 15, 0, 0), (1982, 7, 17, 0, 0))]
+    ref = [_oracle_member(oracle, a, b) for a, b in periods]
+    gpu = []
+    for a, b in periods:
+        m = Speedy(start_date=datetime(*a), end_date=datetime(*b))
+        m.set_bc()
+        gpu.append(m)
+    # different step phases as well: advance member 1 by one step first
+    assert ref[1][0].step(ref[1][1]) == 0
+    assert _speedy.step(gpu[1]._state_cnt, gpu[1]._control_cnt) == 0
+    s = np.array([m._state_cnt for m in gpu], dtype=np.int64)
+    c = np.array([m._control_cnt for m in gpu], dtype=np.int64)
+    for step in range(74):  # two day boundaries for every member
+        for st, ctl in ref:
+            assert st.step(ctl) == 0
+        assert (_speedy.parallel_step(s, c) == 0).all()
+        if step in (0, 35, 36, 73):
+            for i, m in enumerate(gpu):
+                for v in PROG + SURF:
+                    assert relerr(m[v], ref[i][0][v]) < 1e-7, (step, i, v, relerr(m[v], ref[i][0][v]))
+    want = [datetime(1984, 1, 2, 1, 20), datetime(1984, 3, 1, 2, 0), datetime(1982, 7, 17, 1, 20)]
+    for m, w, (st, ctl) in zip(gpu, want, ref):
+        assert m["current_step"] == st["current_step"]
+        assert tuple(ctl.date) == (w.year, w.month, w.day, w.hour, w.minute)
+        assert _speedy.get_model_datetime(m._state_cnt) == tuple(ctl.date)
+
+
+def test_ragged_ensemble_subsets(oracle):
+    """37 members = one full tile + 5 lanes of a second; stepping arbitrary subsets in arbitrary order."""
+    from pyspeedy_b200 import SpeedyEns, _speedy
+
+    ens = SpeedyEns(37, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    ens.set_bc()
+    st, ctl = _oracle_member(oracle, (1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
+    hs, cs = ens.handles()
+    odd = np.arange(1, 37, 2)[::-1].copy()  # reversed order, crosses the tile boundary
+    assert (_speedy.parallel_step(hs[odd], cs[odd]) == 0).all()
+    assert (_speedy.parallel_step(hs[odd], cs[odd]) == 0).all()
+    even = np.arange(0, 37, 2)
+    assert all(ens.members[i]["current_step"] == 0 for i in even)
+    assert (_speedy.parallel_step(hs[even], cs[even]) == 0).all()
+    assert (_speedy.parallel_step(hs[even], cs[even]) == 0).all()
+    assert (_speedy.parallel_step(hs, cs) == 0).all()
+    for _ in range(3):
+        assert st.step(ctl) == 0
+    for i in (0, 1, 31, 32, 35, 36):
+        assert ens.members[i]["current_step"] == 3
+        for v in PROG:
+            assert relerr(ens.members[i][v], st[v]) < 1e-11, (i, v)
+    # identical members stay bit-identical whatever the call pattern was
+    for v in PROG:
+        assert np.array_equal(ens.members[0][v], ens.members[35][v]), v
+        assert np.array_equal(ens.members[0][v], ens.members[36][v]), v
+
+
+def test_failing_member_is_isolated(oracle):
+    """A member whose diagnostics check fails returns -2, keeps its date (speedy.f90:62-66 returns before
+    advance_date) and does not disturb its tile neighbours."""
+    from pyspeedy_b200 import SpeedyEns, _speedy
+
+    ens = SpeedyEns(4, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    ens.set_bc()
+    st, ctl = _oracle_member(oracle, (1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
+    bad = ens.members[2]
+    bad["t"] = bad["t"] * 0.4  # ~100 K: finite everywhere, outside the 180..320 K window of check_diagnostics
+    st_bad, ctl_bad = _oracle_member(oracle, (1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
+    st_bad["t"] = st_bad["t"] * 0.4
+    assert st_bad.step(ctl_bad) == -2
+    hs, cs = ens.handles()
+    err = _speedy.parallel_step(hs, cs)
+    assert [int(x) for x in err] == [0, 0, -2, 0]
+    assert st.step(ctl) == 0
+    for i in (0, 1, 3):
+        for v in PROG:
+            assert relerr(ens.members[i][v], st[v]) < 1e-11, (i, v)
+    # the failed member: step counter incremented, date not advanced
+    assert bad["current_step"] == 1 == st_bad["current_step"]
+    assert tuple(ctl_bad.date) == (1982, 1, 1, 0, 0)
+    assert _speedy.get_model_datetime(bad._state_cnt) == (1982, 1, 1, 0, 0)
+    assert _speedy.get_model_datetime(ens.members[0]._state_cnt) == (1982, 1, 1, 0, 40)
