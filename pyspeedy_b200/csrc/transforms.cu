@@ -233,39 +233,43 @@ __device__ __forceinline__ LdGrid<MODE> make_ld(const Ctx &c, int t, const FwdDe
     return ld;
 }
 
+// CTA = 2 line-groups x 2 warps.  Stage-A item kk is item 0 on inputs kk + 8q with outputs 12kk.. (the eight
+// 12-point problems of passes 1+2 are the same DAG), so each warp runs ONE inlined body four times with shifted
+// pointers; stage B has seven different items, split 4 + 3 between the two warps of a line-group.  Compared with a
+// fully static schedule (30 inlined bodies, 52 KB of code) this removes the instruction-cache stalls that ncu
+// showed as 20 % of the samples of this kernel.
+#ifndef FFTF_UNROLL
+#define FFTF_UNROLL 2
+#endif
+constexpr int kFftfUnroll = FFTF_UNROLL;
 template <int MODE>
 __global__ void __launch_bounds__(128, FFT_MINBLOCKS) k_fft_fwd(const Ctx c, const FwdDesc *__restrict__ descs,
                                                                  long long four_off, int nlg) {
     __shared__ double sm[2 * IX * TILE];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.y, lg0 = blockIdx.x * 2;
-    const int f0 = lg0 / IL, j0 = lg0 - f0 * IL, f1 = (lg0 + 1) / IL, j1 = (lg0 + 1) - f1 * IL;
-    const FwdDesc d0 = descs[f0], d1 = descs[f1];
-    double *s0 = sm + lane, *s1 = sm + IX * TILE + lane;
-    if (warp < 2) {  // stage A: 8 equal items per line-group, 4 per warp
-        const LdGrid<MODE> ld = make_ld<MODE>(c, t, d0, j0, lane);
-        if (warp == 0) fftf_A0(ld, s0), fftf_A1(ld, s0), fftf_A2(ld, s0), fftf_A3(ld, s0);
-        else fftf_A4(ld, s0), fftf_A5(ld, s0), fftf_A6(ld, s0), fftf_A7(ld, s0);
-    } else {
-        const LdGrid<MODE> ld = make_ld<MODE>(c, t, d1, j1, lane);
-        if (warp == 2) fftf_A0(ld, s1), fftf_A1(ld, s1), fftf_A2(ld, s1), fftf_A3(ld, s1);
-        else fftf_A4(ld, s1), fftf_A5(ld, s1), fftf_A6(ld, s1), fftf_A7(ld, s1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lgi = warp >> 1, half = warp & 1;
+    const int t = blockIdx.y, lg = blockIdx.x * 2 + lgi;  // nlg is even
+    const int f = lg / IL, j = lg - f * IL;
+    const FwdDesc d = descs[f];
+    double *s = sm + lgi * (IX * TILE) + lane;
+    {
+        const LdGrid<MODE> ld = make_ld<MODE>(c, t, d, j, lane);
+#pragma unroll kFftfUnroll
+        for (int kk = half * 4; kk < half * 4 + 4; kk++) {
+            LdGrid<MODE> l2 = ld;
+            l2.a += kk * TILE;
+            if (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) l2.b += kk * TILE;
+            fftf_A0(l2, s + 12 * kk * TILE);
+        }
     }
     __syncthreads();
-    // stage B: B0 21, B1..B5 102, B6 34 flops per line-group; item B0 owns row 0 and zeroes row 1 (Im of m = 0)
-    double *four0 = scp(c, t, four_off + (long long)d0.fidx * NFOUR + j0 * M2, lane);
-    double *four1 = scp(c, t, four_off + (long long)d1.fidx * NFOUR + j1 * M2, lane);
-    const StFour st0{four0, c_T.fc[3]}, st1{four1, c_T.fc[3]};
-    if (warp == 0) {
-        fftf_B1(s0, st0), fftf_B2(s0, st0), fftf_B3(s0, st0);
-    } else if (warp == 1) {
-        fftf_B4(s0, st0), fftf_B5(s0, st0), fftf_B1(s1, st1);
-    } else if (warp == 2) {
-        fftf_B2(s1, st1), fftf_B3(s1, st1), fftf_B0(s0, st0), fftf_B6(s0, st0);
-        four0[TILE] = 0.0;  // fourier.f90:117
+    // stage B: B0 21, B1..B5 102, B6 34 flops; item B0 owns row 0 and zeroes row 1 (Im of m = 0, fourier.f90:117)
+    double *four = scp(c, t, four_off + (long long)d.fidx * NFOUR + j * M2, lane);
+    const StFour st{four, c_T.fc[3]};
+    if (half == 0) {
+        fftf_B1(s, st), fftf_B2(s, st), fftf_B3(s, st), fftf_B0(s, st);
+        four[TILE] = 0.0;
     } else {
-        fftf_B4(s1, st1), fftf_B5(s1, st1), fftf_B0(s1, st1), fftf_B6(s1, st1);
-        four1[TILE] = 0.0;
+        fftf_B4(s, st), fftf_B5(s, st), fftf_B6(s, st);
     }
 }
 
