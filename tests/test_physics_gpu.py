@@ -91,3 +91,31 @@ def test_physics_columns(oracle, drv, sw):
         if v == "hfluxn":
             a, b = a[:, :, :2], b[:, :, :2]
         assert relerr(a, b) < 1e-12, (v, relerr(a, b))
+
+
+def test_full_size_column_independence(oracle):
+    """BASELINE config 5 size (1M columns = 224 members x 4608): the physics and every other kernel treat columns /
+    members independently, so a 224-member ensemble of identical members must stay bit-identical member by member
+    (the device-side sum of (x - x_member0)^2 over the members is exactly zero), while member 0 follows the oracle."""
+    from pyspeedy_b200 import SpeedyEns, _speedy
+
+    n = 224
+    ens = SpeedyEns(n, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    ens.set_bc()
+    hs, cs = ens.handles()
+    st = oracle.State(n_months=1)
+    ctl = oracle.Control((1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
+    oracle.load_default_bc(st)
+    assert st.init(ctl) == 0
+    for _ in range(4):  # steps 0..3: two short-wave steps, two long-wave-only steps
+        assert (_speedy.parallel_step(hs, cs) == 0).all()
+        assert st.step(ctl) == 0
+    for v in ["t", "tr", "vor", "div", "ps"]:
+        assert relerr(ens.members[0][v], st[v]) < 1e-11, v
+    for v in ["precnv", "precls", "olr", "tsr", "slrd", "shf", "evap", "ustr", "hfluxn", "tt_rsw", "rad_tau2"]:
+        assert relerr(ens.members[0][v], st[v]) < 1e-9, v
+        _, s2 = _speedy.ensemble_sums(hs, v, shift=ens.members[0][v])  # sum over members of (x - x_member0)^2
+        assert not s2.any(), v
+    for i in (1, 31, 32, 100, 223):
+        for v in ["t", "precnv", "olr"]:
+            assert np.array_equal(ens.members[i][v], ens.members[0][v]), (i, v)
