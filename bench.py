@@ -42,7 +42,9 @@ SPEC_B, FOUR_B, GRID_B = 15872, 23808, 36864
 ALG_BYTES = {
     "legendre_inv": 77 * (SPEC_B + FOUR_B),
     "fft_inv": 77 * (FOUR_B + GRID_B),
-    "fft_fwd": 33 * (GRID_B + FOUR_B) + 40 * (2 * GRID_B + FOUR_B),
+    # 73 Fourier outputs; inputs counted once per launch: 33 plain fields, and for the fused product loaders the
+    # distinct operand fields (u, v, T') + (u, v, q) + (u, v) = 64 grid fields feeding 40 transforms
+    "fft_fwd": 33 * (GRID_B + FOUR_B) + 64 * GRID_B + 40 * FOUR_B,
     "legendre_dir": 73 * (FOUR_B + SPEC_B),
     "grid_dyn": 4608 * (50 + 33) * 8,
     # 158 doubles per column on a long-wave-only step, 167 on a short-wave step (every 3rd): average of 3 steps
