@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k_ens_sums(const Ctx c, long long off, lo
 
 // ---------------------------------------------------------------------------------------- kernel schedules
 // SPDY_FUSED selects the fused Legendre+FFT kernels of fused.cu: 0 = none (default), 1 = both directions,
-// 2 = inverse (spec -> grid) only.  See DESIGN.md section 4 for the measurements behind the default.
+// 2 = inverse (spec -> grid) only, 3 = inverse through the DMMA kernel of fused_mma.cu.  See DESIGN.md section 4 for the measurements behind the default.
 static int fused_mode() {
     static int v = -1;
     if (v < 0) {
@@ -439,6 +439,12 @@ static int fused_mode() {
 static bool use_fused() { return fused_mode() == 1; }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
+    if (fused_mode() == 3) {  // Legendre on the FP64 tensor cores + whole-line FFT, Fourier array in shared memory
+        launch_spec2grid_mma(E.stream, c, d, n);
+        prof_mark(E.stream, PC_FFT_INV);
+        COUNT(1);
+        return;
+    }
     if (use_fused_inv()) {  // Legendre + FFT in one kernel, Fourier array stays in shared memory (fused.cu)
         launch_spec2grid_fused(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);

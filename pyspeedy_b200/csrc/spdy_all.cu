@@ -2,6 +2,7 @@
 // without relocatable device code).  Build: see pyspeedy_b200/csrc/Makefile.
 #include "transforms.cu"
 #include "fused.cu"
+#include "fused_mma.cu"
 #include "dynamics.cu"
 #include "physics.cu"
 #include "surface.cu"

@@ -303,6 +303,22 @@ void build_tables(ConstTables &C, GlobTables &G) {
                     G.cpolj[(m * IY + j) * NX + n] = v;
                 }
         }
+        // ---- pre-swizzled DMMA fragments of the fused spec->grid kernel (fused_mma.cu)
+        {
+            int koff = 0;
+            for (int m = 0; m < MX; m++) {
+                const int ks = (32 - m + 3) / 4, nmax = 31 - m;
+                for (int jq = 0; jq < IY / 4; jq++)
+                    for (int s = 0; s < ks; s++)
+                        for (int L = 0; L < 32; L++) {
+                            const int n = 4 * s + (L & 3), j = 4 * jq + ((L >> 2) & 3), hemi = L >> 4;
+                            double v = (n <= nmax) ? G.cpol[(m * NX + n) * IY + j] : 0.0;
+                            if (hemi && (n & 1)) v = -v;
+                            G.pq_inv[((size_t)jq * PQ_KTOT + koff + s) * 32 + L] = v;
+                        }
+                koff += ks;
+            }
+        }
         // ---- spectral operator tables (spectral.f90:68-110)
         const double re2 = H_REARTH * H_REARTH;
         for (int n = 0; n < NX; n++)

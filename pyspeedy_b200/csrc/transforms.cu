@@ -20,6 +20,7 @@ namespace spdy {
 #define FFT_MINBLOCKS 3
 #endif
 #include "fft96_gen.cuh"
+#include "fft96_reg_gen.cuh"
 
 // ------------------------------------------------------------------------------------------- Legendre inverse
 // One warp = one (field, m-pair); pairs (m, 30-m) balance the triangular truncation: 34 n-terms per pair.
@@ -273,6 +274,44 @@ __global__ void __launch_bounds__(128, FFT_MINBLOCKS) k_fft_fwd(const Ctx c, con
     }
 }
 
+// ------------------------------------------------------------------------- whole-line transforms in registers
+// One thread transforms one (line, member): the 96-value exchange between the two register stages stays in the
+// thread's registers (fft96_reg_gen.cuh), no shared memory, no barrier.  ~210-230 registers, no spills.
+template <class LD, class ST> __device__ __forceinline__ void fftb_line(const LD ld, const ST st) {
+    double x[IX];
+    rfftb_A0(ld, x), rfftb_A1(ld, x), rfftb_A2(ld, x), rfftb_A3(ld, x), rfftb_A4(ld, x), rfftb_A5(ld, x), rfftb_A6(ld, x);
+    rfftb_B0(x, st), rfftb_B1(x, st), rfftb_B2(x, st), rfftb_B3(x, st), rfftb_B4(x, st), rfftb_B5(x, st), rfftb_B6(x, st),
+        rfftb_B7(x, st);
+}
+template <class LD, class ST> __device__ __forceinline__ void fftf_line(const LD ld, const ST st) {
+    double x[IX];
+    rfftf_A0(ld, x), rfftf_A1(ld, x), rfftf_A2(ld, x), rfftf_A3(ld, x), rfftf_A4(ld, x), rfftf_A5(ld, x), rfftf_A6(ld, x),
+        rfftf_A7(ld, x);
+    rfftf_B0(x, st), rfftf_B1(x, st), rfftf_B2(x, st), rfftf_B3(x, st), rfftf_B4(x, st), rfftf_B5(x, st), rfftf_B6(x, st);
+}
+#ifdef FFT_REG
+__global__ void __launch_bounds__(128, 2) k_fft_inv_reg(const Ctx c, const InvDesc *__restrict__ descs, long long four_off, int nlg) {
+    const int lane = threadIdx.x & 31, t = blockIdx.y, lg = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (lg >= nlg) return;
+    const int f = lg / IL, j = lg - f * IL;
+    const LdFour ld{scp(c, t, four_off + (long long)f * NFOUR + j * M2, lane)};
+    const InvDesc d = descs[f];
+    const StGrid st{scp(c, t, d.dst + (long long)j * IX, lane), d.kcos == 1 ? 1.0 : c_T.cosgr[j]};
+    fftb_line(ld, st);
+}
+template <int MODE>
+__global__ void __launch_bounds__(128, 2) k_fft_fwd_reg(const Ctx c, const FwdDesc *__restrict__ descs, long long four_off, int nlg) {
+    const int lane = threadIdx.x & 31, t = blockIdx.y, lg = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (lg >= nlg) return;
+    const int f = lg / IL, j = lg - f * IL;
+    const FwdDesc d = descs[f];
+    const LdGrid<MODE> ld = make_ld<MODE>(c, t, d, j, lane);
+    double *four = scp(c, t, four_off + (long long)d.fidx * NFOUR + j * M2, lane);
+    fftf_line(ld, StFour{four, c_T.fc[3]});
+    four[TILE] = 0.0;  // fourier.f90:117
+}
+#endif
+
 // ------------------------------------------------------------------------------ spectral-space pre-operators
 // uvspec (spectral.f90:190-214) for nlev levels, one warp per complex coefficient (m,n), lane = member
 __device__ __forceinline__ void uvspec_elem(const GlobTables *G, const double *vor, const double *dv, double *u,
@@ -368,11 +407,26 @@ void launch_legendre_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf,
 }
 void launch_fft_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off) {
     const int nlg = nf * IL;
+#ifdef FFT_REG
+    if (nf) k_fft_inv_reg<<<dim3((nlg + 3) / 4, c.ntiles), 128, 0, s>>>(c, d, four_off, nlg);
+#else
     if (nf) k_fft_inv<<<dim3((nlg + 1) / 2, c.ntiles), 128, 0, s>>>(c, d, four_off, nlg);
+#endif
 }
 void launch_fft_fwd(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, int nf, long long four_off) {
     if (!nf) return;
     const int nlg = nf * IL;
+#ifdef FFT_REG
+    const dim3 g((nlg + 3) / 4, c.ntiles);
+    switch (mode) {
+        case FM_PLAIN: k_fft_fwd_reg<FM_PLAIN><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_COS: k_fft_fwd_reg<FM_COS><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_KE: k_fft_fwd_reg<FM_KE><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        case FM_FLUXT: k_fft_fwd_reg<FM_FLUXT><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+        default: k_fft_fwd_reg<FM_FLUX><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
+    }
+}
+#else
     const dim3 g((nlg + 1) / 2, c.ntiles);
     switch (mode) {
         case FM_PLAIN: k_fft_fwd<FM_PLAIN><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
@@ -382,6 +436,7 @@ void launch_fft_fwd(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, in
         default: k_fft_fwd<FM_FLUX><<<g, 128, 0, s>>>(c, d, four_off, nlg); break;
     }
 }
+#endif
 void launch_legendre_dir(cudaStream_t s, const Ctx &c, const FwdOut *o, int nf, long long four_off) {
     if (!nf) return;
     k_legendre_dir<<<dim3(nf * 16, c.ntiles), 128, 0, s>>>(c, o, four_off);

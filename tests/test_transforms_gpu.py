@@ -91,9 +91,11 @@ def test_full_size_properties(drv):
     assert np.array_equal(sa, sa2)
 
 
-def test_fused_transform_path():
-    """The optional fused Legendre+FFT kernels (csrc/fused.cu, SPDY_FUSED=1) against the oracle, in a fresh process
-    because the switch is read when the library initialises; also 3 model steps through the fused path."""
+@pytest.mark.parametrize("mode", ["1", "3"])
+def test_fused_transform_path(mode):
+    """The optional fused Legendre+FFT kernels (csrc/fused.cu: SPDY_FUSED=1; csrc/fused_mma.cu, Legendre on the FP64
+    tensor cores: SPDY_FUSED=3) against the oracle, in a fresh process because the switch is read when the library
+    initialises; also 3 model steps through the fused path."""
     import os
     import subprocess
     import sys
@@ -123,7 +125,7 @@ for v in ("vor", "div", "t", "ps", "tr"):
     assert relerr(m[v], st[v]) < 1e-11, v
 print("fused ok")
 '''
-    env = dict(os.environ, SPDY_FUSED="1")
+    env = dict(os.environ, SPDY_FUSED=mode)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
