@@ -426,13 +426,15 @@ __global__ void __launch_bounds__(256) k_ens_sums(const Ctx c, long long off, lo
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
-// SPDY_FUSED selects the fused Legendre+FFT kernels of fused.cu: 0 = none (default), 1 = both directions,
-// 2 = inverse (spec -> grid) only, 3 = inverse through the DMMA kernel of fused_mma.cu.  See DESIGN.md section 4 for the measurements behind the default.
+// SPDY_FUSED selects the transform kernels: 3 (default) = spec -> grid through the fused DMMA kernel of
+// fused_mma.cu, grid -> spec through the separate FFT and Legendre kernels; 0 = separate kernels both ways;
+// 1 = the first-generation fused kernels of fused.cu both ways, 2 = fused.cu for spec -> grid only.
+// See DESIGN.md section 4 for the measurements behind the default.
 static int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("SPDY_FUSED");
-        v = s ? atoi(s) : 0;
+        v = s ? atoi(s) : 3;
     }
     return v;
 }

@@ -86,6 +86,25 @@ template <int M> __device__ __forceinline__ void mq_mma_store(const MqA<M> &fa, 
     *reinterpret_cast<double2 *>(Sl + (2 * M + 1) * MQ_NM) = make_double2(i0, i1);
 }
 
+// two wavenumbers at once: four independent DMMA chains cover the tensor-pipe latency
+template <int MA, int MB>
+__device__ __forceinline__ void mq_mma_store2(const MqA<MA> &fa, const MqB<MA> &fb, const MqA<MB> &ga, const MqB<MB> &gb,
+                                              double *__restrict__ Sl) {
+    constexpr int KA = MQ_KS(MA), KB = MQ_KS(MB), KMAX = KA > KB ? KA : KB;
+    double r0 = 0.0, r1 = 0.0, i0 = 0.0, i1 = 0.0, p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        if (s < KA) dmma884(r0, r1, fa.a[s], fb.br[s]);
+        if (s < KB) dmma884(p0, p1, ga.a[s], gb.br[s]);
+        if (s < KA) dmma884(i0, i1, fa.a[s], fb.bi[s]);
+        if (s < KB) dmma884(q0, q1, ga.a[s], gb.bi[s]);
+    }
+    *reinterpret_cast<double2 *>(Sl + (2 * MA) * MQ_NM) = make_double2(r0, r1);
+    *reinterpret_cast<double2 *>(Sl + (2 * MA + 1) * MQ_NM) = make_double2(i0, i1);
+    *reinterpret_cast<double2 *>(Sl + (2 * MB) * MQ_NM) = make_double2(p0, p1);
+    *reinterpret_cast<double2 *>(Sl + (2 * MB + 1) * MQ_NM) = make_double2(q0, q1);
+}
+
 // L warp LW owns the units u = LW, LW+4, LW+8, LW+12 (wavenumber pairs (u, 30-u); u = 15 is m = 15 alone): 35-36
 // k-slices per quad for every warp.  The A fragments of wavenumber i+1 are requested before the DMMAs of wavenumber
 // i are issued (explicit software pipeline: with one L warp per scheduler nothing else hides the L2 latency), and
@@ -117,34 +136,22 @@ __device__ __forceinline__ void s2g_mma_L(const Ctx &c, const InvDesc *__restric
             double *Sl = slots + sl * MQ_SLOT + col * MQ_RS + 2 * kk;
             const double *Aq = pq + (size_t)jq * MQ_KTOT * 32;
             MqA<LW> a0;
-            mq_load_a(a0, Aq);
-            if (g >= MQ_NSLOT) mq_bar_sync(MQ_EMPTY0 + sl);
             MqA<30 - LW> a1;
-            mq_load_a(a1, Aq);
-            mq_mma_store(a0, b0, Sl);
             MqA<LW + 4> a2;
-            mq_load_a(a2, Aq);
-            mq_mma_store(a1, b1, Sl);
             MqA<26 - LW> a3;
-            mq_load_a(a3, Aq);
-            mq_mma_store(a2, b2, Sl);
             MqA<LW + 8> a4;
-            mq_load_a(a4, Aq);
-            mq_mma_store(a3, b3, Sl);
             MqA<22 - LW> a5;
-            mq_load_a(a5, Aq);
-            mq_mma_store(a4, b4, Sl);
             MqA<LW + 12> a6;
-            mq_load_a(a6, Aq);
-            mq_mma_store(a5, b5, Sl);
-            if (LW != 3) {
-                MqA<M7> a7;
-                mq_load_a(a7, Aq);
-                mq_mma_store(a6, b6, Sl);
-                mq_mma_store(a7, b7, Sl);
-            } else {
-                mq_mma_store(a6, b6, Sl);
-            }
+            MqA<M7> a7;
+            mq_load_a(a0, Aq), mq_load_a(a1, Aq), mq_load_a(a2, Aq), mq_load_a(a3, Aq);
+            mq_load_a(a4, Aq), mq_load_a(a5, Aq), mq_load_a(a6, Aq);
+            if (LW != 3) mq_load_a(a7, Aq);
+            if (g >= MQ_NSLOT) mq_bar_sync(MQ_EMPTY0 + sl);
+            mq_mma_store2(a0, b0, a1, b1, Sl);
+            mq_mma_store2(a2, b2, a3, b3, Sl);
+            mq_mma_store2(a4, b4, a5, b5, Sl);
+            if (LW != 3) mq_mma_store2(a6, b6, a7, b7, Sl);
+            else mq_mma_store(a6, b6, Sl);
             mq_bar_arrive(MQ_FULL0 + sl);
         }
     }

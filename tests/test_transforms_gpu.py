@@ -91,11 +91,12 @@ def test_full_size_properties(drv):
     assert np.array_equal(sa, sa2)
 
 
-@pytest.mark.parametrize("mode", ["1", "3"])
+@pytest.mark.parametrize("mode", ["0", "1"])
 def test_fused_transform_path(mode):
-    """The optional fused Legendre+FFT kernels (csrc/fused.cu: SPDY_FUSED=1; csrc/fused_mma.cu, Legendre on the FP64
-    tensor cores: SPDY_FUSED=3) against the oracle, in a fresh process because the switch is read when the library
-    initialises; also 3 model steps through the fused path."""
+    """The non-default transform paths (SPDY_FUSED=0: separate Legendre and FFT kernels both ways; 1: the
+    first-generation fused kernels of csrc/fused.cu) against the oracle, in a fresh process because the switch is
+    read when the library initialises; also 3 model steps.  The default (3: csrc/fused_mma.cu for spec -> grid) is
+    what every other test in this suite runs."""
     import os
     import subprocess
     import sys

@@ -388,6 +388,9 @@ def components(outs):
     return sorted((sorted(v) for v in groups.values()), key=lambda v: v[0])
 
 
+LEVEL_ORDER = False
+
+
 def emit(fname, args, outs, load_expr, store_stmt):
     """outs: dict slot -> node.  Returns CUDA source of one item function + flop count."""
     order, seen = [], set()
@@ -405,6 +408,19 @@ def emit(fname, args, outs, load_expr, store_stmt):
 
     for slot in sorted(outs):
         visit(outs[slot])
+    if LEVEL_ORDER:
+        # breadth-first (level) order: consecutive instructions are independent of each other, which matters when a
+        # single warp per scheduler has to cover the FP64 latency on its own (whole-line register variant)
+        depth = {}
+        for n in order:  # `order` is a valid topological order
+            op, a, b = g.nodes[n]
+            if op in ("add", "sub", "mul"):
+                depth[n] = 1 + max(depth[a], depth[b])
+            elif op == "neg":
+                depth[n] = depth[a]
+            else:
+                depth[n] = 0
+        order.sort(key=lambda n: depth[n])
     name = {}
     lines = []
     flops = 0
@@ -432,6 +448,7 @@ def emit(fname, args, outs, load_expr, store_stmt):
 
 
 def main():
+    global LEVEL_ORDER
     out = []
     out.append("// GENERATED by tools/gen_fft96.py -- do not edit.  See that script for the derivation.\n"
                "// 96-point real FFT pair equivalent to the reference's FFTPACK path (fftpack.f90:69-202 with the\n"
@@ -499,13 +516,18 @@ def main():
         report.append("  B%d: %d outputs, %d flops" % (q, len(slots), fl))
     out.append("#define FFTF_NA %d\n#define FFTF_NB %d\n" % (nA, nB))
 
+    if LEVEL_ORDER:  # nested call for the register variant: return the text only
+        return out
     path = os.path.join(ROOT, "pyspeedy_b200/csrc/fft96_gen.cuh")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as fp:
         fp.write("\n".join(out))
     # Register-exchange variant: the same items with the exchange array private to the thread (stride 1), for
     # kernels in which one thread transforms a whole line (fused Legendre+FFT kernels).  Names get an `r` prefix.
-    reg = "\n".join(out).replace("fftb_", "rfftb_").replace("fftf_", "rfftf_").replace(" * FFT_LS]", "]")
+    LEVEL_ORDER = True
+    out_reg = main()
+    LEVEL_ORDER = False
+    reg = "\n".join(out_reg).replace("fftb_", "rfftb_").replace("fftf_", "rfftf_").replace(" * FFT_LS]", "]")
     reg = reg.replace("#define FFTB_NA", "#define RFFTB_NA").replace("#define FFTB_NB", "#define RFFTB_NB")
     reg = reg.replace("#define FFTF_NA", "#define RFFTF_NA").replace("#define FFTF_NB", "#define RFFTF_NB")
     reg = reg.replace("FFT_LS = lane stride (doubles).", "Exchange array private to the thread (stride 1).")
