@@ -441,7 +441,7 @@ static int fused_mode() {
 static bool use_fused() { return fused_mode() == 1; }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
-    if (fused_mode() == 3) {  // Legendre on the FP64 tensor cores + whole-line FFT, Fourier array in shared memory
+    if (fused_mode() >= 3) {  // Legendre on the FP64 tensor cores + whole-line FFT, Fourier array in shared memory
         launch_spec2grid_mma(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
@@ -460,6 +460,12 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
+    if (fused_mode() == 4) {  // FFT + Legendre on the FP64 tensor cores in one kernel per loader mode (fused_mma.cu)
+        for (int m = 0; m < FM_NMODES; m++)
+            if (counts[m]) launch_grid2spec_mma(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
+        prof_mark(E.stream, PC_FFT_FWD);
+        return;
+    }
     if (use_fused()) {
         for (int m = 0; m < FM_NMODES; m++)
             if (counts[m]) launch_grid2spec_fused(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);

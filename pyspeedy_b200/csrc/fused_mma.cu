@@ -219,4 +219,179 @@ void launch_spec2grid_mma(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf
     k_spec2grid_mma<<<nwork < sms ? nwork : sms, 256, MQ_SMEM, s>>>(c, d, nwork);
 }
 
+
+// =================================================================================== forward: grid -> spectral
+// Reference semantics: fourier.f90:90-123 (+ fftpack.f90) and legendre.f90:170-221.
+//
+// The mirror image of the kernel above.  F warps: one thread = one (latitude row, member) line; the grid-point
+// products of tendencies.f90:238-268 are applied while loading (LdGrid<MODE>, transforms.cu), whole-line forward
+// FFT in registers, the 62 Fourier rows go to the slot.  L warps: the Gaussian quadrature as DMMA,
+//     X[n][member] += A[n][(jl,hemi)] * F[(jl,hemi)][member],  A = sgn(hemi,n) * wt(j) * P(m,n,j)
+// with K = the 8 latitude rows of a slot (two k-slices: hemisphere 0 rows, hemisphere 1 rows), M = 8 spectral rows n,
+// accumulators C[n-tile][8 members] kept in registers over the six latitude quads of a work item (20 tiles x {re,im}
+// per L warp = 160 registers) and stored once.  A fragments pre-swizzled on the host (GlobTables::pq_dir).
+__host__ __device__ constexpr int MD_NT(int m) { return ((30 < 31 - m ? 30 : 31 - m) + 1 + 7) / 8; }  // 8-row n-tiles
+__host__ __device__ constexpr int MD_TOFF(int m) { int o = 0; for (int i = 0; i < m; i++) o += MD_NT(i); return o; }
+constexpr int MD_TTOT = MD_TOFF(MX);  // 79
+static_assert(MD_TTOT == PD_TTOT, "GlobTables::pq_dir layout");
+constexpr int MD_RS = M2 * MQ_NM + 4;         // slot row stride: 62 x 64 B + 32 B -> the four rows of a B fragment
+                                              // fall into different bank quarters (conflict-free LDS.64)
+constexpr int MD_SLOT = 8 * MD_RS;
+constexpr int MD_NSLOT = 6;
+constexpr size_t MD_SMEM = (size_t)MD_NSLOT * MD_SLOT * sizeof(double);  // 192,000 bytes
+enum { MD_FULL0 = 1, MD_EMPTY0 = 1 + MD_NSLOT };
+
+template <int M> struct MdC {  // accumulators of wavenumber M: [n-tile][c0, c1], real and imaginary part
+    static constexpr int NT = MD_NT(M);
+    double cr[NT][2], ci[NT][2];
+};
+template <int M> __device__ __forceinline__ void md_zero(MdC<M> &c) {
+#pragma unroll
+    for (int i = 0; i < MD_NT(M); i++) c.cr[i][0] = c.cr[i][1] = c.ci[i][0] = c.ci[i][1] = 0.0;
+}
+//   Aq : fragment table of this quad + lane ; Bl : slot + lane offset (row L%4, member L/4)
+template <int M>
+__device__ __forceinline__ void md_mma(MdC<M> &c, const double *__restrict__ Aq, const double *__restrict__ Bl) {
+    constexpr int NT = MD_NT(M);
+    double a0[NT], a1[NT];
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+        a0[i] = __ldg(Aq + (size_t)((MD_TOFF(M) + i) * 2) * 32);
+        a1[i] = __ldg(Aq + (size_t)((MD_TOFF(M) + i) * 2 + 1) * 32);
+    }
+    const double br0 = Bl[(2 * M) * MQ_NM], br1 = Bl[4 * MD_RS + (2 * M) * MQ_NM];
+    const double bi0 = Bl[(2 * M + 1) * MQ_NM], bi1 = Bl[4 * MD_RS + (2 * M + 1) * MQ_NM];
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+        dmma884(c.cr[i][0], c.cr[i][1], a0[i], br0);
+        dmma884(c.ci[i][0], c.ci[i][1], a0[i], bi0);
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+        dmma884(c.cr[i][0], c.cr[i][1], a1[i], br1);
+        dmma884(c.ci[i][0], c.ci[i][1], a1[i], bi1);
+    }
+}
+//   Xl : spectral output + lane offset (row L/4 of an n-tile, members 2*(L%4), +1); rows up to n = 31 are written
+template <int M> __device__ __forceinline__ void md_store(const MdC<M> &c, double *__restrict__ Xl) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double2 *pr = reinterpret_cast<double2 *>(Xl + (size_t)((2 * M) + M2 * 8 * i) * TILE);
+        double2 *pi = reinterpret_cast<double2 *>(Xl + (size_t)((2 * M + 1) + M2 * 8 * i) * TILE);
+        if (i < MD_NT(M)) {
+            *pr = make_double2(c.cr[i < MD_NT(M) ? i : 0][0], c.cr[i < MD_NT(M) ? i : 0][1]);
+            *pi = make_double2(c.ci[i < MD_NT(M) ? i : 0][0], c.ci[i < MD_NT(M) ? i : 0][1]);
+        } else {  // legendre.f90:206-218: rows outside the nsh2 mask are zero
+            *pr = make_double2(0.0, 0.0), *pi = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+template <int LW>
+__device__ __forceinline__ void g2s_mma_L(const Ctx &c, const FwdDesc *__restrict__ descs, const FwdOut *__restrict__ outs,
+                                          const int nwork, const double *slots, const int lane) {
+    constexpr int M7 = (LW != 3) ? 18 - LW : 15;
+    const int kk = lane & 3, col = lane >> 2;
+    const double *pq = c.G->pq_dir + lane;
+    int g = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int grp = w & 3, t = (w >> 2) % c.ntiles, f = (w >> 2) / c.ntiles;
+        MdC<LW> c0;
+        MdC<30 - LW> c1;
+        MdC<LW + 4> c2;
+        MdC<26 - LW> c3;
+        MdC<LW + 8> c4;
+        MdC<22 - LW> c5;
+        MdC<LW + 12> c6;
+        MdC<M7> c7;
+        md_zero(c0), md_zero(c1), md_zero(c2), md_zero(c3), md_zero(c4), md_zero(c5), md_zero(c6), md_zero(c7);
+#pragma unroll 1
+        for (int jq = 0; jq < IY / 4; jq++, g++) {
+            const int sl = g % MD_NSLOT;
+            const double *Bl = slots + sl * MD_SLOT + kk * MD_RS + col;
+            const double *Aq = pq + (size_t)jq * (MD_TTOT * 2 * 32);
+            asm volatile("bar.sync %0, %1;" ::"r"(MD_FULL0 + sl), "n"(MQ_BARN) : "memory");
+            md_mma(c0, Aq, Bl), md_mma(c1, Aq, Bl), md_mma(c2, Aq, Bl), md_mma(c3, Aq, Bl);
+            md_mma(c4, Aq, Bl), md_mma(c5, Aq, Bl), md_mma(c6, Aq, Bl);
+            if (LW != 3) md_mma(c7, Aq, Bl);
+            asm volatile("bar.arrive %0, %1;" ::"r"(MD_EMPTY0 + sl), "n"(MQ_BARN) : "memory");
+        }
+        double *Xl = refp(c, t, outs[descs[f].fidx].dst, 0) + (size_t)(M2 * col) * TILE + MQ_NM * grp + 2 * kk;
+        md_store(c0, Xl), md_store(c1, Xl), md_store(c2, Xl), md_store(c3, Xl);
+        md_store(c4, Xl), md_store(c5, Xl), md_store(c6, Xl);
+        if (LW != 3) md_store(c7, Xl);
+    }
+}
+
+struct StSlot {
+    double *p;
+    double sc;
+    __device__ __forceinline__ void operator()(int r, double v) const { p[r * MQ_NM] = v * sc; }
+};
+
+template <int MODE>
+__device__ __forceinline__ void g2s_mma_F(const Ctx &c, const FwdDesc *__restrict__ descs, const int nwork, double *slots,
+                                          const int fw, const int lane) {
+    const int hemi = fw & 1, par = fw >> 1, jl = lane >> 3, mem = lane & 7, row = 4 * hemi + jl;
+    int g = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int grp = w & 3, t = (w >> 2) % c.ntiles, f = (w >> 2) / c.ntiles;
+        const FwdDesc d = descs[f];
+#pragma unroll 1
+        for (int jq = 0; jq < IY / 4; jq++, g++) {
+            if ((g & 1) != par) continue;
+            const int sl = g % MD_NSLOT;
+            const int j = 4 * jq + jl, lat = hemi ? j : IL - 1 - j;  // legendre.f90:196-197: fn = row il+1-j, fs = row j
+            const LdGrid<MODE> ld = make_ld<MODE>(c, t, d, lat, MQ_NM * grp + mem);
+            double x[IX];
+            rfftf_A0(ld, x), rfftf_A1(ld, x), rfftf_A2(ld, x), rfftf_A3(ld, x), rfftf_A4(ld, x), rfftf_A5(ld, x),
+                rfftf_A6(ld, x), rfftf_A7(ld, x);
+            if (g >= MD_NSLOT) asm volatile("bar.sync %0, %1;" ::"r"(MD_EMPTY0 + sl), "n"(MQ_BARN) : "memory");
+            double *S = slots + sl * MD_SLOT + row * MD_RS + mem;
+            const StSlot st{S, c_T.fc[3]};
+            rfftf_B0(x, st), rfftf_B1(x, st), rfftf_B2(x, st), rfftf_B3(x, st), rfftf_B4(x, st), rfftf_B5(x, st),
+                rfftf_B6(x, st);
+            S[MQ_NM] = 0.0;  // fourier.f90:117: Im of m = 0
+            __threadfence_block();
+            asm volatile("bar.arrive %0, %1;" ::"r"(MD_FULL0 + sl), "n"(MQ_BARN) : "memory");
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) k_grid2spec_mma(const Ctx c, const FwdDesc *__restrict__ descs,
+                                                          const FwdOut *__restrict__ outs, int nwork) {
+    extern __shared__ __align__(16) double md_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    switch (warp) {
+        case 0: g2s_mma_L<0>(c, descs, outs, nwork, md_sm, lane); break;
+        case 1: g2s_mma_L<1>(c, descs, outs, nwork, md_sm, lane); break;
+        case 2: g2s_mma_L<2>(c, descs, outs, nwork, md_sm, lane); break;
+        case 3: g2s_mma_L<3>(c, descs, outs, nwork, md_sm, lane); break;
+        default: g2s_mma_F<MODE>(c, descs, nwork, md_sm, warp - 4, lane); break;
+    }
+}
+
+template <int MODE> static void launch_g2s_mma_mode(cudaStream_t s, const Ctx &c, const FwdDesc *d, const FwdOut *o, int nf) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_grid2spec_mma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MD_SMEM);
+    }
+    const int nwork = nf * c.ntiles * (TILE / MQ_NM);
+    k_grid2spec_mma<MODE><<<nwork < sms ? nwork : sms, 256, MD_SMEM, s>>>(c, d, o, nwork);
+}
+void launch_grid2spec_mma(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, const FwdOut *o, int nf) {
+    if (!nf) return;
+    switch (mode) {
+        case FM_PLAIN: launch_g2s_mma_mode<FM_PLAIN>(s, c, d, o, nf); break;
+        case FM_COS: launch_g2s_mma_mode<FM_COS>(s, c, d, o, nf); break;
+        case FM_KE: launch_g2s_mma_mode<FM_KE>(s, c, d, o, nf); break;
+        case FM_FLUXT: launch_g2s_mma_mode<FM_FLUXT>(s, c, d, o, nf); break;
+        default: launch_g2s_mma_mode<FM_FLUX>(s, c, d, o, nf); break;
+    }
+}
+
 }  // namespace spdy

@@ -61,12 +61,16 @@ struct ImplTables {  // depends on the time step (implicit.f90:83-218): three in
     double dhsx[KX];
 };
 constexpr int PQ_KTOT = 143;  // sum over m of ceil((32 - m) / 4)
+constexpr int PD_TTOT = 79;   // sum over m of ceil((min(30, 31 - m) + 1) / 8)
 struct GlobTables {
     double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
     double cpolj[MX * IY * NX]; // [m][j][n]  same values, latitude-major slices for the fused transforms
     // DMMA A fragments of the fused spec->grid kernel (fused_mma.cu): [latitude quad 6][k-slice 143][lane 32] =
     // sgn(hemi, n) * P(m, n, j) with n = 4s + lane%4, j = 4jq + (lane/4)%4, hemi = lane/16; 0 outside the nsh2 mask
     double pq_inv[6 * PQ_KTOT * 32];
+    // DMMA A fragments of the fused grid->spec kernel: [quad 6][n-tile 79][k-slice 2][lane 32] =
+    // sgn(hemi, n) * wt(j) * P(m, n, j) with n = 8nt + lane/4, j = 4jq + lane%4, hemi = k-slice; 0 outside the mask
+    double pq_dir[6 * PD_TTOT * 2 * 32];
     double el2[NSPC], elm2[NSPC], trfilt[NSPC], gradym[NSPC], gradyp[NSPC], uvdx[NSPC], uvdym[NSPC], uvdyp[NSPC],
         vddym[NSPC], vddyp[NSPC], dmp[NSPC], dmpd[NSPC], dmps[NSPC];
     double gradx[MX];

@@ -319,6 +319,23 @@ void build_tables(ConstTables &C, GlobTables &G) {
                 koff += ks;
             }
         }
+        // ---- pre-swizzled DMMA fragments of the fused grid->spec kernel (Gaussian weights folded in)
+        {
+            int toff = 0;
+            for (int m = 0; m < MX; m++) {
+                const int nmax = (30 < 31 - m) ? 30 : 31 - m, nt = (nmax + 1 + 7) / 8;
+                for (int jq = 0; jq < IY / 4; jq++)
+                    for (int i = 0; i < nt; i++)
+                        for (int ks = 0; ks < 2; ks++)
+                            for (int L = 0; L < 32; L++) {
+                                const int n = 8 * i + (L >> 2), j = 4 * jq + (L & 3);
+                                double v = (n <= nmax) ? C.wt[j] * G.cpol[(m * NX + n) * IY + j] : 0.0;
+                                if (ks && (n & 1)) v = -v;
+                                G.pq_dir[(((size_t)jq * PD_TTOT + toff + i) * 2 + ks) * 32 + L] = v;
+                            }
+                toff += nt;
+            }
+        }
         // ---- spectral operator tables (spectral.f90:68-110)
         const double re2 = H_REARTH * H_REARTH;
         for (int n = 0; n < NX; n++)
