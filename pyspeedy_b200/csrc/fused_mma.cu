@@ -13,8 +13,8 @@
 //     hemi 0 is grid row il-1-j (even + odd parity sums), hemi 1 is row j (even - odd): folding the sign into A turns
 //     the N/S symmetry into the M dimension, so one C tile holds 4 latitudes x 2 hemispheres = 8 rows and a
 //     shared-memory slot is 8 latitude rows x 62 Fourier rows x 8 members = 31.5 KB (six slots in flight).
-//     A fragments come pre-swizzled (sign and nsh2 mask applied, zero-padded to a multiple of 4 terms) from
-//     GlobTables::pq_inv, one 256-byte row per k-slice and quad.  B fragments are the spectral coefficients of the
+//     A fragments come pre-swizzled (nsh2 mask applied, zero-padded to a multiple of 4 terms) from
+//     GlobTables::pq_inv, one 128-byte row per k-slice and quad; the hemisphere sign is a per-lane mask.  B fragments are the spectral coefficients of the
 //     8 members: each L warp keeps those of its 8 wavenumbers in registers for the whole work item (72 doubles),
 //     so the coefficients cross the L1 once per field instead of once per latitude quad.
 //   F warps: one thread = one (latitude row, member) line, whole-line FFT in registers (fft96_reg_gen.cuh), rows
@@ -70,9 +70,13 @@ template <int M> struct MqA {
     static constexpr int KS = MQ_KS(M);
     double a[KS];
 };
-template <int M> __device__ __forceinline__ void mq_load_a(MqA<M> &f, const double *__restrict__ Aq) {
+// The hemisphere-1 half of a fragment is the hemisphere-0 half with the sign of the odd terms flipped, and the
+// parity of n = 4s + lane%4 is a lane constant: the table holds 16 values per k-slice (18 KB per quad, L1-resident
+// next to 190 KB of shared memory) and the lane applies its sign mask.
+template <int M> __device__ __forceinline__ void mq_load_a(MqA<M> &f, const double *__restrict__ Aq, const long long sgn) {
 #pragma unroll
-    for (int s = 0; s < MQ_KS(M); s++) f.a[s] = __ldg(Aq + (size_t)(MQ_KOFF(M) + s) * 32);
+    for (int s = 0; s < MQ_KS(M); s++)
+        f.a[s] = __longlong_as_double(__double_as_longlong(__ldg(Aq + (size_t)(MQ_KOFF(M) + s) * 16)) ^ sgn);
 }
 //   Sl : slot + lane offset (row L/4, members 2*(L%4), 2*(L%4)+1)
 template <int M> __device__ __forceinline__ void mq_mma_store(const MqA<M> &fa, const MqB<M> &fb, double *__restrict__ Sl) {
@@ -114,7 +118,8 @@ __device__ __forceinline__ void s2g_mma_L(const Ctx &c, const InvDesc *__restric
                                           const int lane) {
     constexpr int M7 = (LW != 3) ? 18 - LW : 15;  // warp 3 has only seven wavenumbers (slot M7 unused there)
     const int kk = lane & 3, col = lane >> 2;
-    const double *pq = c.G->pq_inv + lane;
+    const double *pq = c.G->pq_inv + (lane & 15);
+    const long long sgn = (lane >= 16 && (lane & 1)) ? (long long)0x8000000000000000ull : 0ll;
     int g = 0;  // quad counter, continuous across work items
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int grp = w & 3, t = (w >> 2) % c.ntiles, f = (w >> 2) / c.ntiles;
@@ -134,7 +139,7 @@ __device__ __forceinline__ void s2g_mma_L(const Ctx &c, const InvDesc *__restric
         for (int jq = 0; jq < IY / 4; jq++, g++) {
             const int sl = g % MQ_NSLOT;
             double *Sl = slots + sl * MQ_SLOT + col * MQ_RS + 2 * kk;
-            const double *Aq = pq + (size_t)jq * MQ_KTOT * 32;
+            const double *Aq = pq + (size_t)jq * MQ_KTOT * 16;
             MqA<LW> a0;
             MqA<30 - LW> a1;
             MqA<LW + 4> a2;
@@ -143,9 +148,9 @@ __device__ __forceinline__ void s2g_mma_L(const Ctx &c, const InvDesc *__restric
             MqA<22 - LW> a5;
             MqA<LW + 12> a6;
             MqA<M7> a7;
-            mq_load_a(a0, Aq), mq_load_a(a1, Aq), mq_load_a(a2, Aq), mq_load_a(a3, Aq);
-            mq_load_a(a4, Aq), mq_load_a(a5, Aq), mq_load_a(a6, Aq);
-            if (LW != 3) mq_load_a(a7, Aq);
+            mq_load_a(a0, Aq, sgn), mq_load_a(a1, Aq, sgn), mq_load_a(a2, Aq, sgn), mq_load_a(a3, Aq, sgn);
+            mq_load_a(a4, Aq, sgn), mq_load_a(a5, Aq, sgn), mq_load_a(a6, Aq, sgn);
+            if (LW != 3) mq_load_a(a7, Aq, sgn);
             if (g >= MQ_NSLOT) mq_bar_sync(MQ_EMPTY0 + sl);
             mq_mma_store2(a0, b0, a1, b1, Sl);
             mq_mma_store2(a2, b2, a3, b3, Sl);

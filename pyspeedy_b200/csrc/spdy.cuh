@@ -65,9 +65,9 @@ constexpr int PD_TTOT = 79;   // sum over m of ceil((min(30, 31 - m) + 1) / 8)
 struct GlobTables {
     double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
     double cpolj[MX * IY * NX]; // [m][j][n]  same values, latitude-major slices for the fused transforms
-    // DMMA A fragments of the fused spec->grid kernel (fused_mma.cu): [latitude quad 6][k-slice 143][lane 32] =
-    // sgn(hemi, n) * P(m, n, j) with n = 4s + lane%4, j = 4jq + (lane/4)%4, hemi = lane/16; 0 outside the nsh2 mask
-    double pq_inv[6 * PQ_KTOT * 32];
+    // DMMA A fragments of the fused spec->grid kernel (fused_mma.cu): [latitude quad 6][k-slice 143][16] =
+    // P(m, n, j) with n = 4s + i%4, j = 4jq + i/4 (hemisphere-0 half of the fragment); 0 outside the nsh2 mask
+    double pq_inv[6 * PQ_KTOT * 16];
     // DMMA A fragments of the fused grid->spec kernel: [quad 6][n-tile 79][k-slice 2][lane 32] =
     // sgn(hemi, n) * wt(j) * P(m, n, j) with n = 8nt + lane/4, j = 4jq + lane%4, hemi = k-slice; 0 outside the mask
     double pq_dir[6 * PD_TTOT * 2 * 32];

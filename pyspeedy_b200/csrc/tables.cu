@@ -310,11 +310,10 @@ void build_tables(ConstTables &C, GlobTables &G) {
                 const int ks = (32 - m + 3) / 4, nmax = 31 - m;
                 for (int jq = 0; jq < IY / 4; jq++)
                     for (int s = 0; s < ks; s++)
-                        for (int L = 0; L < 32; L++) {
-                            const int n = 4 * s + (L & 3), j = 4 * jq + ((L >> 2) & 3), hemi = L >> 4;
-                            double v = (n <= nmax) ? G.cpol[(m * NX + n) * IY + j] : 0.0;
-                            if (hemi && (n & 1)) v = -v;
-                            G.pq_inv[((size_t)jq * PQ_KTOT + koff + s) * 32 + L] = v;
+                        for (int L = 0; L < 16; L++) {
+                            const int n = 4 * s + (L & 3), j = 4 * jq + (L >> 2);
+                            G.pq_inv[((size_t)jq * PQ_KTOT + koff + s) * 16 + L] =
+                                (n <= nmax) ? G.cpol[(m * NX + n) * IY + j] : 0.0;
                         }
                 koff += ks;
             }
