@@ -672,6 +672,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     }
     CK(cudaEventRecord(E.ev1, E.stream));
     CK(cudaStreamSynchronize(E.stream));
+    CK(cudaGetLastError());  // a rejected kernel launch is not reported by the synchronisation
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
     for (int i = 0; i < n; i++) failed += (err_out[i] != 0 && err_out[i] != -1) ? 1 : 0;
     return failed;
@@ -723,6 +724,7 @@ static int init_member(Member &m, Control &ctl) {
     run_step_core(c, 1, 1, 0.5 * H_DELT, 0.0, 0);
     run_step_core(c, 1, 2, H_DELT, 0.0, 1);
     CK(cudaStreamSynchronize(E.stream));
+    CK(cudaGetLastError());
     // initialization.f90:85-87: coordinates in default REAL
     for (int k = 0; k < KX; k++) m.lev[k] = (float)E.C.fsg[k];
     for (int k = 0; k < IX; k++) m.lon[k] = 3.75f * (float)k;

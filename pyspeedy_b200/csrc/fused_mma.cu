@@ -21,6 +21,9 @@
 //     read from the slot, 96 grid values stored to HBM.  No exchange buffer, no CTA-wide barrier.  F warps 0,1
 //     (hemisphere 0 / 1 rows) take the even slots, F warps 2,3 the odd ones.
 //   L -> F hand-over per slot through named barriers FULL/EMPTY (bar.arrive / bar.sync, 128 L + 64 F threads).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace spdy {
@@ -218,7 +221,10 @@ void launch_spec2grid_mma(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_spec2grid_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MQ_SMEM);
+        if (cudaFuncSetAttribute(k_spec2grid_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MQ_SMEM) != cudaSuccess) {
+            fprintf(stderr, "speedy_b200: k_spec2grid_mma needs %zu bytes of shared memory per CTA (sm_100a)\n", MQ_SMEM);
+            abort();
+        }
     }
     const int nwork = nf * c.ntiles * (TILE / MQ_NM);
     k_spec2grid_mma<<<nwork < sms ? nwork : sms, 256, MQ_SMEM, s>>>(c, d, nwork);
@@ -383,7 +389,10 @@ template <int MODE> static void launch_g2s_mma_mode(cudaStream_t s, const Ctx &c
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_grid2spec_mma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MD_SMEM);
+        if (cudaFuncSetAttribute(k_grid2spec_mma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MD_SMEM) != cudaSuccess) {
+            fprintf(stderr, "speedy_b200: k_grid2spec_mma needs %zu bytes of shared memory per CTA (sm_100a)\n", MD_SMEM);
+            abort();
+        }
     }
     const int nwork = nf * c.ntiles * (TILE / MQ_NM);
     k_grid2spec_mma<MODE><<<nwork < sms ? nwork : sms, 256, MD_SMEM, s>>>(c, d, o, nwork);
