@@ -83,8 +83,9 @@ __device__ __forceinline__ double fband_at(const double *__restrict__ fb, double
 }
 
 #ifndef PHYS_MINBLOCKS
-#define PHYS_MINBLOCKS 2
+#define PHYS_MINBLOCKS 3
 #endif
+constexpr int PH_SROWS = 6 * KX;  // staged rows per thread: tau2 (32), tt_rsw (8), accumulated T tendency (8)
 __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, const ScratchLayout L, int *__restrict__ dbg) {
     using namespace ph;
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
@@ -93,6 +94,20 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     const bool act = lane_active(c, t, lane);
     const double *fb = c.G->fband;
 #define ST2D(v) (stp(c, t, c.off[v], lane) + e)
+    // Register relief (three CTAs per SM instead of two): the long-wave transmissivities and the short-wave heating
+    // (state, read-only on 2 of 3 steps) are copied straight into shared memory with cp.async while the first half of
+    // the kernel runs, and the accumulated T tendency waits there between the condensation and the final sum.
+    __shared__ double ph_sm[PH_SROWS * 128];
+    double *const sm = ph_sm + threadIdx.x;
+    const bool do_sw = slot(c, t, lane, SL_SW) != 0.0;
+    if (!(do_sw && act)) {  // on short-wave steps the values are produced below
+        const double *pt2 = stp(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp(c, t, c.off[V_tt_rsw], lane) + e;
+#pragma unroll
+        for (int k = 0; k < 4 * KX; k++) cp_async8(sm + k * 128, pt2 + k * lev);
+#pragma unroll
+        for (int k = 0; k < KX; k++) cp_async8(sm + (4 * KX + k) * 128, ptr + k * lev);
+    }
+    cp_async_commit();
 
     // ---- grid-point inputs (physics.f90:89-101)
     double ta[KX], qa[KX], phi[KX];
@@ -120,13 +135,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     // inputs of the later sections (long-wave sweeps, surface fluxes, u/v tendency update): start pulling them into
     // L2 now, so that with only two warps per scheduler those sections wait an L2 hit instead of a DRAM access
     {
-        const bool sw = slot(c, t, lane, SL_SW) != 0.0;
+        const bool sw = do_sw;
         if (!sw) {  // on short-wave steps these are produced below, not read
-            const double *pt2 = stp(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp(c, t, c.off[V_tt_rsw], lane) + e;
-#pragma unroll
-            for (int k = 0; k < 4 * KX; k++) prefetch_l2(pt2 + k * lev);
-#pragma unroll
-            for (int k = 0; k < KX; k++) prefetch_l2(ptr + k * lev);
             const double *pst = stp(c, t, c.off[V_rad_strat_corr], lane) + e;
             prefetch_l2(pst), prefetch_l2(pst + lev), prefetch_l2(ST2D(V_ssrd));
         } else {
@@ -262,6 +272,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         // physics.f90:140-141: ttend = ttend + tt_cnv + tt_lsc
 #pragma unroll
         for (int k = 0; k < KX; k++) tsum[k] = tsum[k] + dtl[k], qsum[k] = qsum[k] + dql[k];
+#pragma unroll
+        for (int k = 0; k < KX; k++) sm[(5 * KX + k) * 128] = tsum[k];
     }
     if (act) {
         *ST2D(V_cbmf) = cbmf;
@@ -273,7 +285,6 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     double *tau2 = stp(c, t, c.off[V_rad_tau2], lane) + e;  // (ix,il,kx,4): element (k, b) at (k + KX*b)*lev
     double *ttrsw = stp(c, t, c.off[V_tt_rsw], lane) + e;
     double *strat = stp(c, t, c.off[V_rad_strat_corr], lane) + e;
-    const bool do_sw = slot(c, t, lane, SL_SW) != 0.0;
     int icltop_out = 0;
     if (do_sw && act) {  // physics.f90:151-169 ; inactive lanes own no state
         // clouds (shortwave_radiation.f90:325-404)
@@ -385,7 +396,10 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
             }
             tau2[(k + KX * 0) * lev] = t1, tau2[(k + KX * 1) * lev] = t2;
             tau2[(k + KX * 2) * lev] = t3, tau2[(k + KX * 3) * lev] = t4;
-            ttrsw[k * lev] = trsw[k] * rps * c_T.grdscp[k];  // physics.f90:166-168
+            const double trk = trsw[k] * rps * c_T.grdscp[k];  // physics.f90:166-168
+            ttrsw[k * lev] = trk;
+            sm[(k + KX * 0) * 128] = t1, sm[(k + KX * 1) * 128] = t2, sm[(k + KX * 2) * 128] = t3, sm[(k + KX * 3) * 128] = t4;
+            sm[(4 * KX + k) * 128] = trk;
         }
         const double eps1 = c_T.ph_eps1;
         strat[0] = *ST2D(V_stratospheric_correction) * psa;
@@ -454,13 +468,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
 
     // ---- downward long-wave (longwave_radiation.f90:16-121)
     double st4a1[KX], st4a2[KX], dfabs[KX], flux[4];
-    double tau[4][KX], trsw_s[KX];  // one batch of independent loads (written above on short-wave steps)
-#pragma unroll
-    for (int jb = 0; jb < 4; jb++)
-#pragma unroll
-        for (int k = 0; k < KX; k++) tau[jb][k] = tau2[(k + KX * jb) * lev];
-#pragma unroll
-    for (int k = 0; k < KX; k++) trsw_s[k] = ttrsw[k * lev];
+    cp_async_wait<0>();  // staged transmissivities (each thread reads only what it copied itself)
+#define TAU(jb, k) sm[((k) + KX * (jb)) * 128]
     {
 #pragma unroll
         for (int k = 0; k < KX - 1; k++) st4a1[k] = ta[k] + c_T.wvi[k][1] * (ta[k + 1] - ta[k]);
@@ -481,7 +490,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         for (int k = 0; k < KX; k++) dfabs[k] = 0.0;
 #pragma unroll
         for (int jb = 0; jb < 2; jb++) {
-            const double emis = 1.0 - tau[jb][0];
+            const double emis = 1.0 - TAU(jb, 0);
             const double brad = fband_at(fb, ta[0], jb) * (st4a1[0] + emis * st4a2[0]);
             flux[jb] = emis * brad;
             dfabs[0] = dfabs[0] - flux[jb];
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         for (int jb = 0; jb < 4; jb++)
 #pragma unroll
             for (int k = 1; k < KX; k++) {
-                const double tk = tau[jb][k];
+                const double tk = TAU(jb, k);
                 const double emis = 1.0 - tk;
                 const double brad = fband_at(fb, ta[k], jb) * (st4a1[k] + emis * st4a2[k]);
                 dfabs[k] = dfabs[k] + flux[jb];
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         for (int jb = 0; jb < 4; jb++)
 #pragma unroll
             for (int k = KX - 1; k >= 1; k--) {
-                const double tk = tau[jb][k];
+                const double tk = TAU(jb, k);
                 const double emis = 1.0 - tk;
                 const double brad = fband_at(fb, ta[k], jb) * (st4a1[k] - emis * st4a2[k]);
                 dfabs[k] = dfabs[k] + flux[jb];
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
             }
 #pragma unroll
         for (int jb = 0; jb < 2; jb++) {
-            const double tk = tau[jb][0];
+            const double tk = TAU(jb, 0);
             const double emis = 1.0 - tk;
             const double brad = fband_at(fb, ta[0], jb) * (st4a1[0] - emis * st4a2[0]);
             dfabs[0] = dfabs[0] + flux[jb];
@@ -639,7 +648,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         *ovtend = *ovtend + vtp;
         oqtend[7 * lev] = qsum[7] + qv[7];
 #pragma unroll
-        for (int k = 0; k < KX; k++) ottend[k * lev] = ((tsum[k] + trsw_s[k]) + dfabs[k] * rps * c_T.grdscp[k]) + tv[k];
+        for (int k = 0; k < KX; k++)
+            ottend[k * lev] = ((sm[(5 * KX + k) * 128] + sm[(4 * KX + k) * 128]) + dfabs[k] * rps * c_T.grdscp[k]) + tv[k];
     }
 
     if (dbg) {
@@ -647,6 +657,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         d[0] = itop, d[(size_t)NG * TILE] = icnv, d[(size_t)2 * NG * TILE] = icltop_out;
     }
 #undef ST2D
+#undef TAU
 }
 
 void launch_physics(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int *dbg) {
