@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/speedy_b200.h"
@@ -608,6 +609,61 @@ static void set_slot_host(const Member &m, int s, double v) {
     CK(cudaStreamSynchronize(E.stream));
 }
 
+// ---- CUDA graphs for launch-bound ensembles ------------------------------------------------------------------
+// One model step of one chunk is ~20 kernel launches; below ~500 members the gaps between them are a visible
+// fraction of the step.  For chunks of at most SPDY_GRAPH_TILES tiles (default 16) the launch sequence of
+// run_model_step is captured once per (chunk, daily / regular step, arena addresses) and replayed.  Every kernel
+// argument is either a device pointer whose CONTENT may change (tile lists, masks, state) or a value that is part
+// of the key; per-member flags (short-wave step, daily forcing) are read on the device.
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+};
+typedef std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, long long, int, int,
+                   int, int>
+    StepGraphKey;
+static std::map<StepGraphKey, StepGraph> g_step_graphs;
+static bool g_eager_done[2] = {false, false};  // statics inside the launchers are initialised by an eager run
+static int graph_max_tiles() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("SPDY_GRAPH_TILES");
+        v = s ? atoi(s) : 16;
+    }
+    return v;
+}
+static void run_chunk_step(int t0, int ntc, bool any_daily) {
+    Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);
+    const bool use_graph = ntc <= graph_max_tiles() && !P.on && g_eager_done[any_daily ? 1 : 0];
+    if (!use_graph) {
+        run_model_step(c, any_daily);
+        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, 0);
+        COUNT(1);
+        g_eager_done[any_daily ? 1 : 0] = true;
+        return;
+    }
+    const StepGraphKey key(E.st, E.scr, E.sst, E.d_tiles, E.d_masks, E.d_err, E.st_elems, E.sst_months, t0, ntc,
+                           any_daily ? 1 : 0);
+    auto it = g_step_graphs.find(key);
+    if (it == g_step_graphs.end()) {
+        StepGraph sg;
+        const long long l0 = g_launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(E.stream, cudaStreamCaptureModeThreadLocal));
+        run_model_step(c, any_daily);
+        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, 0);
+        COUNT(1);
+        CK(cudaStreamEndCapture(E.stream, &graph));
+        CK(cudaGraphInstantiate(&sg.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        sg.launches = g_launches - l0;
+        g_launches = l0;
+        it = g_step_graphs.emplace(key, sg).first;
+    }
+    CK(cudaGraphLaunch(it->second.exec, E.stream));
+    COUNT(it->second.launches);
+}
+
 // bind controls, run nsteps for the listed members; returns per-member first error
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {
     engine_init();
@@ -646,11 +702,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         bool any_daily = false;
         for (size_t q = 0; q < run.size(); q++) any_daily |= (member_of(run[q])->current_step % NSTEPS == 0);
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
-            const int ntc = std::min(E.chunk_tiles, nt - t0);
-            Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);
-            run_model_step(c, any_daily);
-            k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, 0);
-            COUNT(1);
+            run_chunk_step(t0, std::min(E.chunk_tiles, nt - t0), any_daily);
         }
         for (size_t q = 0; q < run.size(); q++) member_of(run[q])->current_step += 1;
         const bool last = (s == nsteps - 1);
