@@ -317,7 +317,8 @@ class SpeedyEns:
         grid-point temperature perturbation of examples/Ensemble_forecast.ipynb to every member."""
         self.members[0].set_bc(bc_file=bc_file, sst_anomaly=sst_anomaly)
         s, _ = self.handles()
-        _speedy.clone_state(int(s[0]), s[1:])
+        if len(s) > 1:
+            _speedy.clone_state(int(s[0]), s[1:])
         for m in self.members[1:]:
             m._initialized_bc = m._initialized_ssta = True
         if perturb_sigma:
