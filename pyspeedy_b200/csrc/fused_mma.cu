@@ -354,6 +354,21 @@ __device__ __forceinline__ void g2s_mma_F(const Ctx &c, const FwdDesc *__restric
             const int sl = g % MD_NSLOT;
             const int j = 4 * jq + jl, lat = hemi ? j : IL - 1 - j;  // legendre.f90:196-197: fn = row il+1-j, fs = row j
             const LdGrid<MODE> ld = make_ld<MODE>(c, t, d, lat, MQ_NM * grp + mem);
+            {   // this warp's next task (two quads further on, possibly in its next work item): pull its grid rows
+                // into L2 now -- the whole-line FFT leaves no registers to prefetch into
+                int nq = jq + 2, nw = w;
+                if (nq >= IY / 4) nq -= IY / 4, nw += gridDim.x;
+                if (nw < nwork) {
+                    const int ngrp = nw & 3, nt = (nw >> 2) % c.ntiles, nf = (nw >> 2) / c.ntiles;
+                    const int nj = 4 * nq + jl, nlat = hemi ? nj : IL - 1 - nj;
+                    const LdGrid<MODE> ln = make_ld<MODE>(c, nt, nw == w ? d : descs[nf], nlat, MQ_NM * ngrp + mem);
+#pragma unroll 8
+                    for (int i = 0; i < IX; i++) {
+                        prefetch_l2(ln.a + i * TILE);
+                        if (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) prefetch_l2(ln.b + i * TILE);
+                    }
+                }
+            }
             double x[IX];
             rfftf_A0(ld, x), rfftf_A1(ld, x), rfftf_A2(ld, x), rfftf_A3(ld, x), rfftf_A4(ld, x), rfftf_A5(ld, x),
                 rfftf_A6(ld, x), rfftf_A7(ld, x);
