@@ -110,3 +110,31 @@ def test_failing_member_is_isolated(oracle):
     assert tuple(ctl_bad.date) == (1982, 1, 1, 0, 0)
     assert _speedy.get_model_datetime(bad._state_cnt) == (1982, 1, 1, 0, 0)
     assert _speedy.get_model_datetime(ens.members[0]._state_cnt) == (1982, 1, 1, 0, 40)
+
+
+def test_sst_anomaly_across_month_boundary(oracle):
+    """A non-zero SST anomaly (the reference's default run reads one from sst_anomaly.nc, which is not shipped here)
+    interpolated in time across a month boundary: monthly_interp (interpolation.f90:17-36), the month index carried
+    by the control parameters (model_control.f90:113-163) and the coupler's per-day cache."""
+    from pyspeedy_b200 import Speedy, _speedy
+
+    rng = np.random.default_rng(11)
+    ssta = np.asfortranarray(rng.normal(0.0, 1.5, size=(96, 48, 4)))  # Dec 1981 .. Mar 1982
+    st = oracle.State(n_months=2)
+    ctl = oracle.Control((1982, 1, 30, 0, 0), (1982, 2, 2, 0, 0))
+    oracle.load_default_bc(st)
+    st["sst_anom"] = ssta
+    assert st.init(ctl) == 0
+    m = Speedy(start_date=datetime(1982, 1, 30), end_date=datetime(1982, 2, 2))
+    m.set_bc(sst_anomaly=ssta)
+    checks = ["sstan_am", "sst_am", "sst_om", "tice_om", "ssti_om", "t", "ps", "vor"]
+    for v in checks:
+        assert relerr(m[v], st[v]) < 1e-9, ("init", v, relerr(m[v], st[v]))
+    assert np.abs(m["sstan_am"]).max() > 0.5  # the anomaly is really in use
+    for step in range(100):  # 1982-01-30 00:00 + 100 x 40 min = 02-01 18:40
+        assert st.step(ctl) == 0
+        assert _speedy.step(m._state_cnt, m._control_cnt) == 0
+        if step in (0, 35, 36, 71, 72, 73, 99):
+            for v in checks:
+                assert relerr(m[v], st[v]) < 1e-8, (step, v, relerr(m[v], st[v]))
+    assert _speedy.get_model_datetime(m._state_cnt) == tuple(ctl.date) == (1982, 2, 1, 18, 40)
