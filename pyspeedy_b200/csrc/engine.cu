@@ -435,13 +435,19 @@ static int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("SPDY_FUSED");
-        v = s ? atoi(s) : 3;
+        v = s ? atoi(s) : 5;
     }
     return v;
 }
 static bool use_fused() { return fused_mode() == 1; }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
+    if (fused_mode() == 5) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps (fused_mma2.cu)
+        launch_spec2grid_mma2(E.stream, c, d, n);
+        prof_mark(E.stream, PC_FFT_INV);
+        COUNT(1);
+        return;
+    }
     if (fused_mode() >= 3) {  // Legendre on the FP64 tensor cores + whole-line FFT, Fourier array in shared memory
         launch_spec2grid_mma(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);

@@ -43,7 +43,9 @@ enum { MQ_FULL0 = 1, MQ_EMPTY0 = 1 + MQ_NSLOT };  // named barriers 1..6 and 7..
 
 __device__ __forceinline__ void mq_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(MQ_BARN) : "memory"); }
 __device__ __forceinline__ void mq_bar_arrive(int id) {
+#ifdef MQ_FENCE
     __threadfence_block();
+#endif
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(MQ_BARN) : "memory");
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {

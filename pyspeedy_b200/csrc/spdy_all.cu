@@ -3,6 +3,7 @@
 #include "transforms.cu"
 #include "fused.cu"
 #include "fused_mma.cu"
+#include "fused_mma2.cu"
 #include "dynamics.cu"
 #include "physics.cu"
 #include "surface.cu"
