@@ -17,8 +17,11 @@ __device__ constexpr double D_ROB = FL(0.05), D_WIL = FL(0.53);
 // ------------------------------------------------------------------------------------ grid-point dynamics
 // tendencies.f90:132-224.  Inputs: ug, vg, tg, vorg, divg, trg (level j2), px, py.  Outputs: utend, vtend,
 // ttend, trtend and the grid field whose transform is psdt.
-__global__ void __launch_bounds__(128) k_grid_dyn(const Ctx c, const ScratchLayout L) {
-    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+// FUSE: the column is handed on to the physics of the same thread (k_physics<true>, physics.cu): the T and tracer
+// tendencies and the lowest-level u, v tendencies stay in registers instead of making a round trip through HBM.
+template <bool FUSE>
+__device__ __forceinline__ void grid_dyn_column(const Ctx &c, const ScratchLayout &L, const int t, const int lane, const int q,
+                                                double (&tt)[KX], double (&qt)[KX], double &ut8, double &vt8) {
     const int j = q / IX;
     const size_t e = (size_t)q * TILE, lev = (size_t)NG * TILE;
     const double *pu = scp(c, t, L.ug, lane) + e, *pv = scp(c, t, L.vg, lane) + e, *pt = scp(c, t, L.tg, lane) + e,
@@ -56,24 +59,44 @@ __global__ void __launch_bounds__(128) k_grid_dyn(const Ctx c, const ScratchLayo
 #pragma unroll
     for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (u[k] - u[k - 1]);
 #pragma unroll
-    for (int k = 0; k < KX; k++) ou[k * lev] = v[k] * vo[k] - tgg[k] * D_RGAS * px - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+    for (int k = 0; k < KX; k++) {
+        const double r = v[k] * vo[k] - tgg[k] * D_RGAS * px - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+        if (FUSE && k == KX - 1) ut8 = r;
+        else ou[k * lev] = r;
+    }
     // meridional wind :187-194
 #pragma unroll
     for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (v[k] - v[k - 1]);
 #pragma unroll
-    for (int k = 0; k < KX; k++) ov[k * lev] = -u[k] * vo[k] - tgg[k] * D_RGAS * py - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+    for (int k = 0; k < KX; k++) {
+        const double r = -u[k] * vo[k] - tgg[k] * D_RGAS * py - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+        if (FUSE && k == KX - 1) vt8 = r;
+        else ov[k * lev] = r;
+    }
     // temperature :197-209
 #pragma unroll
     for (int k = 1; k < KX; k++) tmp[k] = sigdt[k] * (tgg[k] - tgg[k - 1]) + sigm[k] * (c_T.tref[k] - c_T.tref[k - 1]);
 #pragma unroll
-    for (int k = 0; k < KX; k++)
-        ot[k * lev] = tgg[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k] + c_T.fsgr[k] * tgg[k] * (sigdt[k + 1] + sigdt[k]) +
-                      c_T.tref3[k] * (sigm[k + 1] + sigm[k]) + D_AKAP * (T[k] * puv[k] - tgg[k] * dmean);
+    for (int k = 0; k < KX; k++) {
+        const double r = tgg[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k] + c_T.fsgr[k] * tgg[k] * (sigdt[k + 1] + sigdt[k]) +
+                         c_T.tref3[k] * (sigm[k + 1] + sigm[k]) + D_AKAP * (T[k] * puv[k] - tgg[k] * dmean);
+        if (FUSE) tt[k] = r;
+        else ot[k * lev] = r;
+    }
     // tracer :212-224 (temp(:,:,2:3) = 0)
 #pragma unroll
     for (int k = 1; k < KX; k++) tmp[k] = (k <= 2) ? 0.0 : sigdt[k] * (tr[k] - tr[k - 1]);
 #pragma unroll
-    for (int k = 0; k < KX; k++) oq[k * lev] = tr[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+    for (int k = 0; k < KX; k++) {
+        const double r = tr[k] * d[k] - (tmp[k + 1] + tmp[k]) * c_T.dhsr[k];
+        if (FUSE) qt[k] = r;
+        else oq[k * lev] = r;
+    }
+}
+__global__ void __launch_bounds__(128) k_grid_dyn(const Ctx c, const ScratchLayout L) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    double tt[KX], qt[KX], ut8, vt8;
+    grid_dyn_column<false>(c, L, t, lane, q, tt, qt, ut8, vt8);
 }
 
 // -------------------------------------------------------------------------- spectral tendencies + time step

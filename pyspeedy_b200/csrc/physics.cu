@@ -85,20 +85,45 @@ __device__ __forceinline__ double fband_at(const double *__restrict__ fb, double
 #ifndef PHYS_MINBLOCKS
 #define PHYS_MINBLOCKS 3
 #endif
-constexpr int PH_SROWS = 6 * KX;  // staged rows per thread: tau2 (32), tt_rsw (8), accumulated T tendency (8)
+constexpr int PH_SROWS = 7 * KX;  // staged rows per thread: tau2 (32), tt_rsw (8), (accumulated) T tendency (8), q tendency (8)
+// FUSE: the grid-point dynamics of the same column (grid_dyn_column, dynamics.cu; tendencies.f90:132-224) run first in
+// this thread and hand their T / tracer tendencies (and the lowest-level u, v tendencies) over in registers, in the
+// order the reference accumulates them (physics.f90 adds to the dynamical tendencies): 34 loads and 34 stores per
+// column never reach HBM.
+template <bool FUSE>
 __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, const ScratchLayout L, int *__restrict__ dbg) {
     using namespace ph;
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     const int j = q / IX;
     const size_t e = (size_t)q * TILE, lev = (size_t)NG * TILE;
-    const bool act = lane_active(c, t, lane);
-    const double *fb = c.G->fband;
 #define ST2D(v) (stp(c, t, c.off[v], lane) + e)
     // Register relief (three CTAs per SM instead of two): the long-wave transmissivities and the short-wave heating
     // (state, read-only on 2 of 3 steps) are copied straight into shared memory with cp.async while the first half of
     // the kernel runs, and the accumulated T tendency waits there between the condensation and the final sum.
-    __shared__ double ph_sm[PH_SROWS * 128];
+    // The dynamical T / tracer tendencies that the physics adds to (needed only after the convection) arrive the same
+    // way: first cp.async group, so they cost neither registers nor a stall at the top of the kernel.
+    extern __shared__ __align__(16) double ph_sm[];  // PH_SROWS x 128 doubles (56 KB: dynamic, three CTAs per SM)
     double *const sm = ph_sm + threadIdx.x;
+    double *ottend = scp(c, t, L.ttend, lane) + e, *oqtend = scp(c, t, L.trtend, lane) + e;
+    if (!FUSE) {
+#pragma unroll
+        for (int k = 0; k < KX; k++) cp_async8(sm + (5 * KX + k) * 128, ottend + k * lev);
+#pragma unroll
+        for (int k = 0; k < KX; k++) cp_async8(sm + (6 * KX + k) * 128, oqtend + k * lev);
+    }
+    cp_async_commit();
+    // ---- grid-point inputs (physics.f90:89-101): scratch addresses do not depend on the tile list, so these loads are
+    // in flight while the first access to the state arena (below) still waits for its tile index
+    double ta[KX], qa[KX], phi[KX];
+    {
+        const double *pt = scp(c, t, L.ptg, lane) + e, *pq = scp(c, t, L.pqg, lane) + e, *pp = scp(c, t, L.pphig, lane) + e;
+#pragma unroll
+        for (int k = 0; k < KX; k++) ta[k] = pt[k * lev], qa[k] = pq[k * lev], phi[k] = pp[k * lev];
+    }
+    const double ua8 = *(scp(c, t, L.pug8, lane) + e), va8 = *(scp(c, t, L.pvg8, lane) + e);
+    const double psl = *(scp(c, t, L.pslg, lane) + e);
+    const bool act = lane_active(c, t, lane);
+    const double *fb = c.G->fband;
     const bool do_sw = slot(c, t, lane, SL_SW) != 0.0;
     if (!(do_sw && act)) {  // on short-wave steps the values are produced below
         const double *pt2 = stp(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp(c, t, c.off[V_tt_rsw], lane) + e;
@@ -108,16 +133,9 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         for (int k = 0; k < KX; k++) cp_async8(sm + (4 * KX + k) * 128, ptr + k * lev);
     }
     cp_async_commit();
-
-    // ---- grid-point inputs (physics.f90:89-101)
-    double ta[KX], qa[KX], phi[KX];
-    {
-        const double *pt = scp(c, t, L.ptg, lane) + e, *pq = scp(c, t, L.pqg, lane) + e, *pp = scp(c, t, L.pphig, lane) + e;
 #pragma unroll
-        for (int k = 0; k < KX; k++) ta[k] = pt[k * lev], qa[k] = fmax(pq[k * lev], 0.0), phi[k] = pp[k * lev];
-    }
-    const double ua8 = *(scp(c, t, L.pug8, lane) + e), va8 = *(scp(c, t, L.pvg8, lane) + e);
-    const double psa = fast_exp(*(scp(c, t, L.pslg, lane) + e));
+    for (int k = 0; k < KX; k++) qa[k] = fmax(qa[k], 0.0);
+    const double psa = fast_exp(psl);
     const double rps = fast_rcp(psa);
     double se[KX], rh[KX], qsat[KX];
 #pragma unroll
@@ -126,11 +144,9 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         qsat[k] = qsat_of(ta[k], psa, c_T.fsg[k]);
         rh[k] = qa[k] * fast_rcp(qsat[k]);
     }
-    // T and q tendencies are accumulated in registers in the reference's order of additions and written once
-    double *ottend = scp(c, t, L.ttend, lane) + e, *oqtend = scp(c, t, L.trtend, lane) + e;
-    double tsum[KX], qsum[KX];
-#pragma unroll
-    for (int k = 0; k < KX; k++) tsum[k] = ottend[k * lev], qsum[k] = oqtend[k * lev];
+    // T and q tendencies are accumulated in the reference's order of additions and written once
+    double tsum[KX], qsum[KX], ut8 = 0.0, vt8 = 0.0;
+    if (FUSE) grid_dyn_column<true>(c, L, t, lane, q, tsum, qsum, ut8, vt8);
 
     // inputs of the later sections (long-wave sweeps, surface fluxes, u/v tendency update): start pulling them into
     // L2 now, so that with only two warps per scheduler those sections wait an L2 hit instead of a DRAM access
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         prefetch_l2(ST2D(V_phis0)), prefetch_l2(ST2D(V_fmask_land)), prefetch_l2(ST2D(V_forog)), prefetch_l2(ST2D(V_sst_am));
         prefetch_l2(ST2D(V_alb_land)), prefetch_l2(ST2D(V_alb_sea)), prefetch_l2(ST2D(V_snowc));
         prefetch_l2(ST2D(V_land_temp)), prefetch_l2(ST2D(V_soil_avail_water));
-        prefetch_l2(scp(c, t, L.utend, lane) + e + 7 * lev), prefetch_l2(scp(c, t, L.vtend, lane) + e + 7 * lev);
+        if (!FUSE) prefetch_l2(scp(c, t, L.utend, lane) + e + 7 * lev), prefetch_l2(scp(c, t, L.vtend, lane) + e + 7 * lev);
     }
 
     // ---- deep convection (convection.f90:27-253)
@@ -235,6 +251,11 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         }
     }
     // physics.f90:128-131,140-141 ; tt_cnv(1) stays 0
+    if (!FUSE) {
+        cp_async_wait<1>();  // first group: the dynamical tendencies (each thread reads only what it copied itself)
+#pragma unroll
+        for (int k = 0; k < KX; k++) tsum[k] = sm[(5 * KX + k) * 128], qsum[k] = sm[(6 * KX + k) * 128];
+    }
     tsum[0] = tsum[0] + 0.0, qsum[0] = qsum[0] + 0.0;
 #pragma unroll
     for (int k = 1; k < KX; k++) {
@@ -644,8 +665,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         tv[7] = tv[7] + shf3 * rps * c_T.grdscp[7];
         qv[7] = qv[7] + evap3 * rps * c_T.grdsig[7];
         double *outend = scp(c, t, L.utend, lane) + e + 7 * lev, *ovtend = scp(c, t, L.vtend, lane) + e + 7 * lev;
-        *outend = *outend + utp;
-        *ovtend = *ovtend + vtp;
+        *outend = (FUSE ? ut8 : *outend) + utp;
+        *ovtend = (FUSE ? vt8 : *ovtend) + vtp;
         oqtend[7 * lev] = qsum[7] + qv[7];
 #pragma unroll
         for (int k = 0; k < KX; k++)
@@ -660,8 +681,19 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
 #undef TAU
 }
 
-void launch_physics(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int *dbg) {
-    k_physics<<<dim3(NG / 4, c.ntiles), 128, 0, s>>>(c, L, dbg);
+constexpr int PH_SMEM = PH_SROWS * 128 * 8;
+template <bool FUSE> static void launch_physics_t(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int *dbg) {
+    static bool init = false;
+    if (!init) {
+        if (cudaFuncSetAttribute(k_physics<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM) != cudaSuccess) {
+            fprintf(stderr, "speedy_b200: k_physics needs %d bytes of shared memory per CTA (sm_100a)\n", PH_SMEM);
+            abort();
+        }
+        init = true;
+    }
+    k_physics<FUSE><<<dim3(NG / 4, c.ntiles), 128, PH_SMEM, s>>>(c, L, dbg);
 }
+void launch_dyn_physics(cudaStream_t s, const Ctx &c, const ScratchLayout &L) { launch_physics_t<true>(s, c, L, nullptr); }
+void launch_physics(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int *dbg) { launch_physics_t<false>(s, c, L, dbg); }
 
 }  // namespace spdy
