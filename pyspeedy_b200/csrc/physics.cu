@@ -85,7 +85,8 @@ __device__ __forceinline__ double fband_at(const double *__restrict__ fb, double
 #ifndef PHYS_MINBLOCKS
 #define PHYS_MINBLOCKS 3
 #endif
-constexpr int PH_SROWS = 7 * KX;  // staged rows per thread: tau2 (32), tt_rsw (8), (accumulated) T tendency (8), q tendency (8)
+constexpr int PH_SROWS = 7 * KX + 2;  // staged rows per thread: tau2 (32), tt_rsw (8), (accumulated) T tendency (8), q
+                                     // tendency (8), lowest-level u and v tendencies (2)
 // FUSE: the grid-point dynamics of the same column (grid_dyn_column, dynamics.cu; tendencies.f90:132-224) run first in
 // this thread and hand their T / tracer tendencies (and the lowest-level u, v tendencies) over in registers, in the
 // order the reference accumulates them (physics.f90 adds to the dynamical tendencies): 34 loads and 34 stores per
@@ -102,14 +103,19 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     // the kernel runs, and the accumulated T tendency waits there between the condensation and the final sum.
     // The dynamical T / tracer tendencies that the physics adds to (needed only after the convection) arrive the same
     // way: first cp.async group, so they cost neither registers nor a stall at the top of the kernel.
-    extern __shared__ __align__(16) double ph_sm[];  // PH_SROWS x 128 doubles (56 KB: dynamic, three CTAs per SM)
+    extern __shared__ __align__(16) double ph_sm[];  // PH_SROWS x 128 doubles (58 KB: dynamic, three CTAs per SM)
     double *const sm = ph_sm + threadIdx.x;
+    // request the tile index and the lane mask now: every state address below depends on them
+    const unsigned mask0 = __ldg(c.masks + t);
+    const int tile0 = __ldg(c.tiles + t);
     double *ottend = scp(c, t, L.ttend, lane) + e, *oqtend = scp(c, t, L.trtend, lane) + e;
     if (!FUSE) {
 #pragma unroll
         for (int k = 0; k < KX; k++) cp_async8(sm + (5 * KX + k) * 128, ottend + k * lev);
 #pragma unroll
         for (int k = 0; k < KX; k++) cp_async8(sm + (6 * KX + k) * 128, oqtend + k * lev);
+        cp_async8(sm + (7 * KX) * 128, scp(c, t, L.utend, lane) + e + 7 * lev);
+        cp_async8(sm + (7 * KX + 1) * 128, scp(c, t, L.vtend, lane) + e + 7 * lev);
     }
     cp_async_commit();
     // ---- grid-point inputs (physics.f90:89-101): scratch addresses do not depend on the tile list, so these loads are
@@ -122,9 +128,9 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     }
     const double ua8 = *(scp(c, t, L.pug8, lane) + e), va8 = *(scp(c, t, L.pvg8, lane) + e);
     const double psl = *(scp(c, t, L.pslg, lane) + e);
-    const bool act = lane_active(c, t, lane);
+    const bool act = (mask0 >> lane) & 1u;
     const double *fb = c.G->fband;
-    const bool do_sw = slot(c, t, lane, SL_SW) != 0.0;
+    const bool do_sw = *(c.st + ((long long)tile0 * c.st_elems + c.off_slots + SL_SW) * TILE + lane) != 0.0;
     if (!(do_sw && act)) {  // on short-wave steps the values are produced below
         const double *pt2 = stp(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp(c, t, c.off[V_tt_rsw], lane) + e;
 #pragma unroll
@@ -162,7 +168,6 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         prefetch_l2(ST2D(V_phis0)), prefetch_l2(ST2D(V_fmask_land)), prefetch_l2(ST2D(V_forog)), prefetch_l2(ST2D(V_sst_am));
         prefetch_l2(ST2D(V_alb_land)), prefetch_l2(ST2D(V_alb_sea)), prefetch_l2(ST2D(V_snowc));
         prefetch_l2(ST2D(V_land_temp)), prefetch_l2(ST2D(V_soil_avail_water));
-        if (!FUSE) prefetch_l2(scp(c, t, L.utend, lane) + e + 7 * lev), prefetch_l2(scp(c, t, L.vtend, lane) + e + 7 * lev);
     }
 
     // ---- deep convection (convection.f90:27-253)
@@ -665,8 +670,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         tv[7] = tv[7] + shf3 * rps * c_T.grdscp[7];
         qv[7] = qv[7] + evap3 * rps * c_T.grdsig[7];
         double *outend = scp(c, t, L.utend, lane) + e + 7 * lev, *ovtend = scp(c, t, L.vtend, lane) + e + 7 * lev;
-        *outend = (FUSE ? ut8 : *outend) + utp;
-        *ovtend = (FUSE ? vt8 : *ovtend) + vtp;
+        *outend = (FUSE ? ut8 : sm[(7 * KX) * 128]) + utp;
+        *ovtend = (FUSE ? vt8 : sm[(7 * KX + 1) * 128]) + vtp;
         oqtend[7 * lev] = qsum[7] + qv[7];
 #pragma unroll
         for (int k = 0; k < KX; k++)
