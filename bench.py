@@ -217,10 +217,12 @@ def run_b200(args):
     l0 = lib.spdy_kernel_launches()
     if rank == 0:
         sampler.start()
+    lib.spdy_profiler_start()  # cudaProfilerStart/Stop: `ncu --profile-from-start off` lists exactly the timed launches
     t0 = time.perf_counter()
     err = _speedy.run_steps(s, c, args.steps)
     torch.cuda.synchronize()
     t_local = time.perf_counter() - t0
+    lib.spdy_profiler_stop()
     dev_ms = float(lib.spdy_last_elapsed_ms())
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -283,7 +285,7 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=36, warmup=1)
+        r = cpu_reference_run(steps=72, warmup=1, members=8 * (os.cpu_count() or 8))
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['members']} members x {r['steps']} steps in {r['seconds']:.1f} s, oracle (C++ restatement; "
                          "the reference Fortran cannot be built in this image), OpenMP dynamic over members"}

@@ -57,6 +57,9 @@ int spdy_synchronize(void);
 /* elapsed device time (ms) of the last spdy_run_steps / spdy_parallel_step call, CUDA events on the launch stream */
 float spdy_last_elapsed_ms(void);
 long long spdy_kernel_launches(void);       /* kernels launched by this library so far */
+/* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` sees only a bracketed region */
+int spdy_profiler_start(void);
+int spdy_profiler_stop(void);
 /* The member's model date as the device calendar holds it (control_params%model_datetime of the bound control,
    model_control.f90:113-163); out = {year, month, day, hour, minute}.  Returns 0, or -1 for an unknown handle. */
 int spdy_get_model_datetime(int64_t state, int *out);
