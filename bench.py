@@ -108,7 +108,9 @@ def cpu_reference_run(steps, warmup, members=None):
     """The oracle driven like parallel_step (speedy_driver.f90.j2:58-79) on all host threads."""
     from oracle import oracle as O
 
-    cores = O.max_threads()
+    # all host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would leave the CPU
+    # arm on one core, so the thread count is taken from the affinity mask and passed explicitly
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else O.max_threads()
     members = members or 4 * cores
     st0 = O.State(n_months=1)
     ctl0 = O.Control((1982, 1, 1, 0, 0), (1982, 1, 11, 0, 0))
@@ -122,10 +124,10 @@ def cpu_reference_run(steps, warmup, members=None):
         t[:, :, :, 0] += 1e-4 * rng.standard_normal(t[:, :, :, 0].shape) * (np.abs(t[:, :, :, 0]) > 0)
         s["t"] = t
     for _ in range(warmup):
-        assert (O.parallel_step(states, ctls) == 0).all()
+        assert (O.parallel_step(states, ctls, cores) == 0).all()
     t0 = time.perf_counter()
     for _ in range(steps):
-        assert (O.parallel_step(states, ctls) == 0).all()
+        assert (O.parallel_step(states, ctls, cores) == 0).all()
     dt = time.perf_counter() - t0
     return dict(value=members * steps / NSTEPS_DAY / dt, seconds=dt, cores=cores, members=members, steps=steps)
 
@@ -285,7 +287,7 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=72, warmup=1, members=8 * (os.cpu_count() or 8))
+        r = cpu_reference_run(steps=72, warmup=1, members=8 * len(os.sched_getaffinity(0)))
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['members']} members x {r['steps']} steps in {r['seconds']:.1f} s, oracle (C++ restatement; "
                          "the reference Fortran cannot be built in this image), OpenMP dynamic over members"}
