@@ -86,3 +86,28 @@ def test_bench_algorithmic_bytes():
     spec.loader.exec_module(b)
     assert b.SPEC_B == 31 * 32 * 16 and b.GRID_B == 96 * 48 * 8 and b.FOUR_B == 62 * 48 * 8
     assert b.ALG_BYTES["legendre_inv"] == 77 * 39680 and b.ALG_BYTES["fft_inv"] == 77 * 60672
+
+
+def test_fortran_shim_in_sync_with_registry(tmp_path):
+    """integration/speedy_driver_b200.f90 (the iso_c_binding host side) is the generator's
+    output for the packaged registry: one get/set/shape triple per array, every bind(C) name is declared in the
+    header, free-form line length respected."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "integration", "speedy_driver_b200.f90")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_fortran_shim.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before
+    header = open(os.path.join(root, "include", "speedy_b200.h")).read()
+    for name in set(re.findall(r'bind\(C, name="(\w+)"\)', before)):
+        assert re.search(r"\b%s\(" % name, header), name
+    assert max(len(line) for line in before.splitlines()) <= 132
+    reg = json.load(open(os.path.join(root, "pyspeedy_b200", "data", "model_state.json")))
+    for e in reg:
+        assert "subroutine get_%s(" % e["name"] in before and "subroutine set_%s(" % e["name"] in before
+        assert "subroutine is_array_%s(" % e["name"] in before
+        if e["shape"] is not None:
+            assert "subroutine get_%s_shape(" % e["name"] in before
