@@ -255,17 +255,15 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
                 }
         }
     }
-    // physics.f90:128-131,140-141 ; tt_cnv(1) stays 0
-    if (!FUSE) {
-        cp_async_wait<1>();  // first group: the dynamical tendencies (each thread reads only what it copied itself)
-#pragma unroll
-        for (int k = 0; k < KX; k++) tsum[k] = sm[(5 * KX + k) * 128], qsum[k] = sm[(6 * KX + k) * 128];
-    }
-    tsum[0] = tsum[0] + 0.0, qsum[0] = qsum[0] + 0.0;
+    // physics.f90:128-131,140-141 ; tt_cnv(1) stays 0.  The convective terms wait in registers until the dynamical
+    // tendencies (first cp.async group) are needed: the sums keep the reference's order ((dyn + cnv) + lsc) but the
+    // wait for the copy moves behind the condensation.
+    double tcnv[KX], qcnv[KX];
+    tcnv[0] = 0.0, qcnv[0] = 0.0;
 #pragma unroll
     for (int k = 1; k < KX; k++) {
-        tsum[k] = tsum[k] + dfse[k] * rps * c_T.grdscp[k];
-        qsum[k] = qsum[k] + dfqa[k] * rps * c_T.grdsig[k];
+        tcnv[k] = dfse[k] * rps * c_T.grdscp[k];
+        qcnv[k] = dfqa[k] * rps * c_T.grdsig[k];
     }
     const int icnv = KX - itop;
 
@@ -296,8 +294,13 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         for (int k = 1; k < KX; k++) precls = precls - (c_T.dhs[k] * prg) * dql[k];
         precls = precls * psa;
         // physics.f90:140-141: ttend = ttend + tt_cnv + tt_lsc
+        if (!FUSE) {
+            cp_async_wait<1>();  // first group: the dynamical tendencies (each thread reads only what it copied itself)
 #pragma unroll
-        for (int k = 0; k < KX; k++) tsum[k] = tsum[k] + dtl[k], qsum[k] = qsum[k] + dql[k];
+            for (int k = 0; k < KX; k++) tsum[k] = sm[(5 * KX + k) * 128], qsum[k] = sm[(6 * KX + k) * 128];
+        }
+#pragma unroll
+        for (int k = 0; k < KX; k++) tsum[k] = (tsum[k] + tcnv[k]) + dtl[k], qsum[k] = (qsum[k] + qcnv[k]) + dql[k];
 #pragma unroll
         for (int k = 0; k < KX; k++) sm[(5 * KX + k) * 128] = tsum[k];
     }
