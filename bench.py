@@ -260,6 +260,8 @@ def run_b200(args):
     alg = dict(ALG_BYTES)
     if prof["legendre_inv"] == 0.0:  # default path: spec -> grid is ONE fused kernel, the Fourier array stays on chip
         alg["fft_inv"], alg["legendre_inv"] = 77 * (SPEC_B + GRID_B), 0
+    if prof["legendre_dir"] == 0.0:  # default path: grid -> spec is one fused kernel per loader mode as well
+        alg["fft_fwd"], alg["legendre_dir"] = (33 + 64) * GRID_B + 73 * SPEC_B, 0
     cls = max(alg, key=lambda k: prof[k])
     achieved = alg[cls] * n_prof / (prof[cls] * 1e-3) / 1e9
     total_prof = sum(prof.values())

@@ -435,7 +435,7 @@ static int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("SPDY_FUSED");
-        v = s ? atoi(s) : 5;
+        v = s ? atoi(s) : 6;
     }
     return v;
 }
@@ -453,7 +453,7 @@ static bool fuse_dyn_physics() {
 }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
-    if (fused_mode() == 5) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps (fused_mma2.cu)
+    if (fused_mode() == 5 || fused_mode() == 6) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps
         launch_spec2grid_mma2(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
@@ -478,6 +478,12 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
+    if (fused_mode() == 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
+        for (int m = 0; m < FM_NMODES; m++)
+            if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
+        prof_mark(E.stream, PC_FFT_FWD);
+        return;
+    }
     if (fused_mode() == 4) {  // FFT + Legendre on the FP64 tensor cores in one kernel per loader mode (fused_mma.cu)
         for (int m = 0; m < FM_NMODES; m++)
             if (counts[m]) launch_grid2spec_mma(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);

@@ -335,6 +335,26 @@ void build_tables(ConstTables &C, GlobTables &G) {
                 toff += nt;
             }
         }
+        // ---- parity-pure fragments of the second-generation fused grid->spec kernel (fused_mma2.cu): the N/S fold
+        //      (legendre.f90:196-203) is done on the Fourier rows, so a tile needs one k-slice instead of two
+        {
+            int toff = 0;
+            for (int m = 0; m < MX; m++) {
+                const int nmax = (30 < 31 - m) ? 30 : 31 - m;
+                const int cnt[2] = {nmax / 2 + 1, (nmax + 1) / 2};
+                const int nt[2] = {(cnt[0] + 7) / 8, (cnt[1] + 7) / 8};
+                for (int jq = 0; jq < IY / 4; jq++)
+                    for (int par = 0; par < 2; par++)
+                        for (int i = 0; i < nt[par]; i++)
+                            for (int L = 0; L < 32; L++) {
+                                const int n = par + 2 * (8 * i + (L >> 2)), j = 4 * jq + (L & 3);
+                                G.pq_dir2[((size_t)jq * PD2_TTOT + toff + (par ? nt[0] : 0) + i) * 32 + L] =
+                                    (n <= nmax) ? C.wt[j] * G.cpol[(m * NX + n) * IY + j] : 0.0;
+                            }
+                toff += nt[0] + nt[1];
+            }
+            if (toff != PD2_TTOT) abort();
+        }
         // ---- spectral operator tables (spectral.f90:68-110)
         const double re2 = H_REARTH * H_REARTH;
         for (int n = 0; n < NX; n++)
