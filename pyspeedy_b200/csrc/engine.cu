@@ -453,7 +453,7 @@ static bool fuse_dyn_physics() {
 }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
-    if (fused_mode() == 5 || fused_mode() == 6) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps
+    if (fused_mode() >= 5) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps
         launch_spec2grid_mma2(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
@@ -478,7 +478,7 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
-    if (fused_mode() == 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
+    if (fused_mode() >= 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
         for (int m = 0; m < FM_NMODES; m++)
             if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
         prof_mark(E.stream, PC_FFT_FWD);
