@@ -118,7 +118,9 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
     Ctx c = ws_ctx(n);
     ws_set_kcos(kcos);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
-    if (fused_mode() >= 5) {
+    if (fused_mode() >= 7) {
+        launch_spec2grid_mma3(E.stream, c, W.d_inv, 1);
+    } else if (fused_mode() >= 5) {
         launch_spec2grid_mma2(E.stream, c, W.d_inv, 1);
     } else if (fused_mode() >= 3) {
         launch_spec2grid_mma(E.stream, c, W.d_inv, 1);

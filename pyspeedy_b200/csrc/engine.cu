@@ -435,7 +435,7 @@ static int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("SPDY_FUSED");
-        v = s ? atoi(s) : 6;
+        v = s ? atoi(s) : 7;
     }
     return v;
 }
@@ -453,6 +453,12 @@ static bool fuse_dyn_physics() {
 }
 static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
+    if (fused_mode() >= 7) {  // third generation: parity-pure DMMA over latitude octets (fused_mma3.cu)
+        launch_spec2grid_mma3(E.stream, c, d, n);
+        prof_mark(E.stream, PC_FFT_INV);
+        COUNT(1);
+        return;
+    }
     if (fused_mode() >= 5) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps
         launch_spec2grid_mma2(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);

@@ -62,6 +62,7 @@ struct ImplTables {  // depends on the time step (implicit.f90:83-218): three in
 };
 constexpr int PQ_KTOT = 143;  // sum over m of ceil((32 - m) / 4)
 constexpr int PD_TTOT = 79;   // sum over m of ceil((min(30, 31 - m) + 1) / 8)
+constexpr int PQ2_KTOT = 155; // sum over m of the 4-term k-slices of even n plus those of odd n (fused_mma3.cu)
 constexpr int PD2_TTOT = 93;  // sum over m of the 8-row tiles of even n plus those of odd n (fused_mma2.cu)
 struct GlobTables {
     double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
@@ -71,6 +72,9 @@ struct GlobTables {
     double pq_inv[6 * PQ_KTOT * 16];
     // DMMA A fragments of the fused grid->spec kernel: [quad 6][n-tile 79][k-slice 2][lane 32] =
     // sgn(hemi, n) * wt(j) * P(m, n, j) with n = 8nt + lane/4, j = 4jq + lane%4, hemi = k-slice; 0 outside the mask
+    // parity-pure DMMA A fragments of the third-generation spec->grid kernel: [latitude octet 3][k-slice 155][lane 32] =
+    // P(m, n, j) with n = parity + 2 * (4s + lane%4), j = 8jo + lane/4; per m the even-n slices, then the odd-n slices
+    double pq_inv2[3 * PQ2_KTOT * 32];
     double pq_dir[6 * PD_TTOT * 2 * 32];
     // parity-pure DMMA A fragments of the second-generation grid->spec kernel: [quad 6][tile 93][lane 32] =
     // wt(j) * P(m, n, j) with n = parity + 2 * (8 * i + lane/4), j = 4jq + lane%4; per m the even-n tiles, then the odd-n tiles

@@ -4,6 +4,7 @@
 #include "fused.cu"
 #include "fused_mma.cu"
 #include "fused_mma2.cu"
+#include "fused_mma3.cu"
 #include "dynamics.cu"
 #include "physics.cu"
 #include "surface.cu"

@@ -335,6 +335,24 @@ void build_tables(ConstTables &C, GlobTables &G) {
                 toff += nt;
             }
         }
+        // ---- parity-pure fragments of the third-generation fused spec->grid kernel (fused_mma3.cu): M = 8 latitudes
+        {
+            int koff = 0;
+            for (int m = 0; m < MX; m++) {
+                const int nmax = 31 - m, cnt[2] = {(32 - m + 1) / 2, (32 - m) / 2};
+                const int ks[2] = {(cnt[0] + 3) / 4, (cnt[1] + 3) / 4};
+                for (int jo = 0; jo < IY / 8; jo++)
+                    for (int par = 0; par < 2; par++)
+                        for (int s = 0; s < ks[par]; s++)
+                            for (int L = 0; L < 32; L++) {
+                                const int n = par + 2 * (4 * s + (L & 3)), j = 8 * jo + (L >> 2);
+                                G.pq_inv2[((size_t)jo * PQ2_KTOT + koff + (par ? ks[0] : 0) + s) * 32 + L] =
+                                    (n <= nmax) ? G.cpol[(m * NX + n) * IY + j] : 0.0;
+                            }
+                koff += ks[0] + ks[1];
+            }
+            if (koff != PQ2_KTOT) abort();
+        }
         // ---- parity-pure fragments of the second-generation fused grid->spec kernel (fused_mma2.cu): the N/S fold
         //      (legendre.f90:196-203) is done on the Fourier rows, so a tile needs one k-slice instead of two
         {

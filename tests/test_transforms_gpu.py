@@ -91,7 +91,7 @@ def test_full_size_properties(drv):
     assert np.array_equal(sa, sa2)
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "3", "4", "5"])
+@pytest.mark.parametrize("mode", ["0", "1", "3", "4", "5", "6"])
 def test_fused_transform_path(mode):
     """The non-default transform paths (SPDY_FUSED=0: separate Legendre and FFT kernels both ways; 1: the
     first-generation fused kernels of csrc/fused.cu) against the oracle, in a fresh process because the switch is
