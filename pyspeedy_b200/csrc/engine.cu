@@ -116,6 +116,8 @@ struct Engine {
     // transform descriptor lists
     InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2
     FwdDesc *d_fwd[FM_NMODES] = {};
+    FwdDesc *d_fwd_all = nullptr;  // all fields of the step in one list (FwdDesc::mode set), two-operand modes first
+    int n_fwd_all = 0;
     int n_fwd[FM_NMODES] = {};
     FwdOut *d_out = nullptr;
     InvDesc *d_inv_tmp = nullptr;
@@ -184,6 +186,15 @@ static void build_descriptor_lists() {
         E.n_fwd[m] = (int)f[m].size();
         CK(cudaMalloc(&E.d_fwd[m], f[m].size() * sizeof(FwdDesc)));
         CK(cudaMemcpy(E.d_fwd[m], f[m].data(), f[m].size() * sizeof(FwdDesc), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<FwdDesc> all;
+        const int order[FM_NMODES] = {FM_FLUXT, FM_FLUX, FM_KE, FM_PLAIN, FM_COS};
+        for (int q = 0; q < FM_NMODES; q++)
+            for (FwdDesc d : f[order[q]]) d.mode = order[q], d.pad = 0, all.push_back(d);
+        E.n_fwd_all = (int)all.size();
+        CK(cudaMalloc(&E.d_fwd_all, all.size() * sizeof(FwdDesc)));
+        CK(cudaMemcpy(E.d_fwd_all, all.data(), all.size() * sizeof(FwdDesc), cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&E.d_out, outs.size() * sizeof(FwdOut)));
     CK(cudaMemcpy(E.d_out, outs.data(), outs.size() * sizeof(FwdOut), cudaMemcpyHostToDevice));
@@ -484,6 +495,12 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     COUNT(2);
 }
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
+    if (fused_mode() >= 7 && lists == E.d_fwd) {  // the step's 73 fields in ONE launch of the fused forward kernel
+        launch_grid2spec_mma2(E.stream, c, FM_ALL, E.d_fwd_all, outs, E.n_fwd_all);
+        COUNT(1);
+        prof_mark(E.stream, PC_FFT_FWD);
+        return;
+    }
     if (fused_mode() >= 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
         for (int m = 0; m < FM_NMODES; m++)
             if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);

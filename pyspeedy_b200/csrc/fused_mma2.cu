@@ -258,7 +258,8 @@ void launch_spec2grid_mma2(cudaStream_t s, const Ctx &c, const InvDesc *d, int n
 //     Gaussian quadrature as DMMA over the six quads of a work item (10 n-tiles x {re,im} per warp = 80 registers).
 constexpr int G2_NS = 2;                       // slots
 template <int MODE> struct G2Cfg {
-    static constexpr int NOP = (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX) ? 2 : 1;
+    // FM_ALL: one launch for a mixed list (FwdDesc::mode per field), ring entries sized for two operands
+    static constexpr int NOP = (MODE == FM_KE || MODE == FM_FLUXT || MODE == FM_FLUX || MODE == FM_ALL) ? 2 : 1;
     static constexpr int NB = (NOP == 2) ? 3 : 6;  // input buffer ring (passes): what fits next to the slots
     static constexpr size_t SMEM = ((size_t)G2_NS * MD_SLOT + (size_t)NB * NOP * M2_XH) * sizeof(double) + 64;
 };
@@ -389,13 +390,14 @@ __device__ __forceinline__ void g2s2_F(const Ctx &c, const FwdDesc *__restrict__
         const int lat0 = hemi ? 4 * jq : IL - 4 - 4 * jq;
         const unsigned mbar = mbar0 + 8 * (p % G2_NB);
         const unsigned dst = (unsigned)__cvta_generic_to_shared(bufs + (size_t)(p % G2_NB) * NOP * M2_XH);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(NOP * M2_XH * 8) : "memory");
+        const bool two = (MODE == FM_ALL) ? (d.mode >= FM_KE) : (NOP == 2);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((two ? 2 : 1) * M2_XH * 8) : "memory");
         const int ea = (int)((long long)t * c.scr_elems + (d.a & ~REF_SCR));
         asm volatile(
             "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
             "l"(tmap), "r"(mbar), "r"(MQ_NM * grp), "r"(lat0), "r"(0), "r"(0), "r"(ea)
             : "memory");
-        if (NOP == 2) {
+        if (two) {
             const int eb = (int)((long long)t * c.scr_elems + (d.b & ~REF_SCR));
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
@@ -419,10 +421,17 @@ __device__ __forceinline__ void g2s2_F(const Ctx &c, const FwdDesc *__restrict__
                 double *ba = bufs + (size_t)(p % G2_NB) * NOP * M2_XH + lane;
                 g2_mbar_wait(mbar0 + 8 * (p % G2_NB), (p / G2_NB) & 1);
                 {   // stage A: item fw on rows 12fw .. 12fw+11, in place in operand buffer a
-                    LdBox<MODE> ld;
-                    ld.a = ba + 12 * fw * 32, ld.b = ld.a + (NOP == 2 ? M2_XH : 0);
-                    ld.k0 = d.k0, ld.sc = (d.kcos == 3) ? c_T.cosgr2[lat] : c_T.cosgr[lat];
-                    fftf_A0(ld, ba + 12 * fw * 32);
+                    double *sa = ba + 12 * fw * 32;
+                    const double sc = (d.kcos == 3) ? c_T.cosgr2[lat] : c_T.cosgr[lat];
+                    if (MODE != FM_ALL) {
+                        fftf_A0(LdBox<MODE>{sa, sa + (NOP == 2 ? M2_XH : 0), d.k0, sc}, sa);
+                    } else {  // warp-uniform switch on the field's loader mode
+                        if (d.mode == FM_PLAIN) fftf_A0(LdBox<FM_PLAIN>{sa, sa, d.k0, sc}, sa);
+                        else if (d.mode == FM_COS) fftf_A0(LdBox<FM_COS>{sa, sa, d.k0, sc}, sa);
+                        else if (d.mode == FM_KE) fftf_A0(LdBox<FM_KE>{sa, sa + M2_XH, d.k0, sc}, sa);
+                        else if (d.mode == FM_FLUXT) fftf_A0(LdBox<FM_FLUXT>{sa, sa + M2_XH, d.k0, sc}, sa);
+                        else fftf_A0(LdBox<FM_FLUX>{sa, sa + M2_XH, d.k0, sc}, sa);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 m2_sync(G2_GRP, 256);
@@ -497,6 +506,7 @@ template <int MODE> static void launch_g2s2_mode(cudaStream_t s, const Ctx &c, c
 void launch_grid2spec_mma2(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, const FwdOut *o, int nf) {
     if (!nf) return;
     switch (mode) {
+        case FM_ALL: launch_g2s2_mode<FM_ALL>(s, c, d, o, nf); break;  // mixed list, FwdDesc::mode per field
         case FM_PLAIN: launch_g2s2_mode<FM_PLAIN>(s, c, d, o, nf); break;
         case FM_COS: launch_g2s2_mode<FM_COS>(s, c, d, o, nf); break;
         case FM_KE: launch_g2s2_mode<FM_KE>(s, c, d, o, nf); break;

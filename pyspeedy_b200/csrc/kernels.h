@@ -12,12 +12,14 @@ struct InvDesc {
     int pad;
 };
 // forward transform: loader modes (grid-point products fused into the FFT loads)
-enum FwdMode { FM_PLAIN = 0, FM_COS = 1, FM_KE = 2, FM_FLUXT = 3, FM_FLUX = 4, FM_NMODES = 5 };
+enum FwdMode { FM_PLAIN = 0, FM_COS = 1, FM_KE = 2, FM_FLUXT = 3, FM_FLUX = 4, FM_NMODES = 5, FM_ALL = 5 };
 struct FwdDesc {
     FieldRef a, b;  // grid fields (96,48)
     double k0;      // FM_FLUXT: reference temperature subtracted from b
     int kcos;       // 2: cosgr, 3: cosgr2 (spectral.f90:229-242)
     int fidx;       // Fourier slot / index into the FwdOut list
+    int mode;       // loader mode of this field in a mixed list (FM_ALL launches of the fused forward kernel)
+    int pad;
 };
 struct FwdOut {
     FieldRef dst;   // spectral field (62,32)
