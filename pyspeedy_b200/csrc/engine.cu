@@ -604,7 +604,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT);
     launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx, dump);
     prof_mark(E.stream, PC_SPEC_STEP);
-    COUNT(1);
+    COUNT(2);  // k_spec_step_vq + k_spec_step_dt
 }
 
 // do_single_step (speedy.f90:20-74) for one chunk of tiles
