@@ -300,8 +300,8 @@ int spdy_profiler_start(void) { return (int)cudaProfilerStart(); }
 int spdy_profiler_stop(void) { return (int)cudaProfilerStop(); }
 }
 
-static double *g_sums = nullptr;
-static size_t g_sums_n = 0;
+static double *g_sums = nullptr, *g_part = nullptr;
+static size_t g_sums_n = 0, g_part_n = 0;
 int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **out, size_t *nelem) {
     engine_init();
     if (var < 0 || var >= SPDY_NVARS || E.off[var] < 0) return -1;
@@ -311,11 +311,17 @@ int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, con
         CK(cudaMalloc(&g_sums, 2 * n * sizeof(double)));
         g_sums_n = n;
     }
-    CK(cudaMemsetAsync(g_sums, 0, 2 * n * sizeof(double), E.stream));
     const int nt = prepare_members(states, n_members);
+    const int groups = (nt + ENS_TG - 1) / ENS_TG;
+    if ((size_t)groups * 2 * n > g_part_n) {
+        if (g_part) CK(cudaFree(g_part));
+        g_part_n = (size_t)groups * 2 * n;
+        CK(cudaMalloc(&g_part, g_part_n * sizeof(double)));
+    }
     Ctx c = make_ctx(E.d_tiles, E.d_masks, nt);
-    k_ens_sums<<<(int)((n + 7) / 8), 256, 0, E.stream>>>(c, E.off[var], n, shift_dev, g_sums, g_sums + n);
-    COUNT(1);
+    k_ens_sums<<<dim3((unsigned)((n + 7) / 8), groups), 256, 0, E.stream>>>(c, E.off[var], n, shift_dev, g_part);
+    k_ens_reduce<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(g_part, groups, n, g_sums, g_sums + n);
+    COUNT(2);
     CK(cudaStreamSynchronize(E.stream));
     *out = g_sums;
     *nelem = (size_t)n;

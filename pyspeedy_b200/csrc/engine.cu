@@ -419,22 +419,39 @@ __global__ void k_set_slot(const Ctx c, int s, double v) {
     const int lane = threadIdx.x, t = blockIdx.x;
     if (lane_active(c, t, lane)) slot(c, t, lane, s) = v;
 }
-// ensemble partial sums: per grid element, sum over the active lanes of all chunk tiles
+// ensemble partial sums.  Stage 1: warp per (grid element, group of ENS_TG tiles), lane = member: the
+// group's loads are issued together (a tile is 375 MB away from the next one: one load at a time is pure DRAM latency),
+// warp-shuffle reduction over the lanes, one partial per (group, element).  Stage 2: thread per element adds the
+// partials in group order -- deterministic, unlike atomics.
+constexpr int ENS_TG = 8;
 __global__ void __launch_bounds__(256) k_ens_sums(const Ctx c, long long off, long long n, const double *shift,
-                                                  double *sum, double *sumsq) {
-    const int lane = threadIdx.x & 31;
+                                                  double *part /* [groups][2][n] */) {
+    const int lane = threadIdx.x & 31, g = blockIdx.y;
     const long long i = blockIdx.x * 8ll + (threadIdx.x >> 5);
     if (i >= n) return;
     const double sh = shift ? shift[i] : 0.0;
+    double x[ENS_TG];
+    bool act[ENS_TG];
+#pragma unroll
+    for (int q = 0; q < ENS_TG; q++) {
+        const int t = g * ENS_TG + q;
+        act[q] = t < c.ntiles && lane_active(c, t, lane);
+        x[q] = act[q] ? *(stp(c, t, off + i, lane)) : 0.0;
+    }
     double s1 = 0.0, s2 = 0.0;
-    for (int t = 0; t < c.ntiles; t++)
-        if (lane_active(c, t, lane)) {
-            const double x = *(stp(c, t, off + i, lane));
-            s1 += x;
-            s2 += (x - sh) * (x - sh);
-        }
+#pragma unroll
+    for (int q = 0; q < ENS_TG; q++)
+        if (act[q]) s1 += x[q], s2 += (x[q] - sh) * (x[q] - sh);
     for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    if (lane == 0) sum[i] += s1, sumsq[i] += s2;
+    if (lane == 0) part[((size_t)g * 2) * n + i] = s1, part[((size_t)g * 2 + 1) * n + i] = s2;
+}
+__global__ void __launch_bounds__(256) k_ens_reduce(const double *__restrict__ part, int groups, long long n, double *sum,
+                                                    double *sumsq) {
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int g = 0; g < groups; g++) s1 += part[((size_t)g * 2) * n + i], s2 += part[((size_t)g * 2 + 1) * n + i];
+    sum[i] = s1, sumsq[i] = s2;
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
