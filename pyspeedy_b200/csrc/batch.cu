@@ -137,7 +137,9 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
 int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
-    if (use_fused()) {
+    if (fused_mode() >= 6) {  // the model step's default forward kernel (the workspace is a scratch arena)
+        launch_grid2spec_mma2(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
+    } else if (use_fused()) {
         launch_grid2spec_fused(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
     } else {
         launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);

@@ -119,3 +119,31 @@ def test_full_size_column_independence(oracle):
     for i in (1, 31, 32, 100, 223):
         for v in ["t", "precnv", "olr"]:
             assert np.array_equal(ens.members[i][v], ens.members[0][v]), (i, v)
+
+
+def test_fused_dynamics_physics_path():
+    """SPDY_FUSE_PHYS=1 (grid-point dynamics and column physics of a column in one kernel, tendencies handed over in
+    registers) against the oracle: three model steps, in a fresh process because the switch is read once."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from util import relerr
+from oracle import oracle as O
+from pyspeedy_b200 import Speedy, _speedy
+from datetime import datetime
+st = O.State(n_months=1); ctl = O.Control((1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0)); O.load_default_bc(st); assert st.init(ctl) == 0
+m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)); m.set_bc()
+for _ in range(3):
+    assert st.step(ctl) == 0 and _speedy.step(m._state_cnt, m._control_cnt) == 0
+for v in ("vor", "div", "t", "ps", "tr"):
+    assert relerr(m[v], st[v]) < 1e-11, v
+print("fused physics ok")
+'''
+    env = dict(os.environ, SPDY_FUSE_PHYS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fused physics ok" in out.stdout, out.stdout + out.stderr
