@@ -144,6 +144,11 @@ __device__ __forceinline__ void s2g3_L(const Ctx &c, const InvDesc *__restrict__
     }
 }
 
+struct StExch1 {  // StExchK (fused_mma2.cu) without the scaling
+    double *p;
+    __device__ __forceinline__ void operator()(int i, double v) const { p[(i >> 3) * 32] = v; }
+};
+
 // F warp fw of 8: hemisphere fw >> 2, item share fw & 3; lane = (jl, member); two passes (halves of the hemisphere's
 // eight latitudes) per octet.  Hemisphere 1 rows 8 + 4*half + jl hold latitude 8jo + 4*half + jl; hemisphere 0 is read in
 // reverse (slot row 4*half + 3 - jl = latitude il-4-8jo-4*half + jl) so that the four latitudes of a pass ascend with jl:
@@ -180,9 +185,14 @@ __device__ __forceinline__ void s2g3_F(const Ctx &c, const InvDesc *__restrict__
                 if (half == 1) m2_arrive(P3_EMPTY0 + sl, 512);  // this warp has read its share of the slot completely
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 m2_sync(P3_GRP0 + 2 * hemi, 128);
-                const double sc = d.kcos == 1 ? 1.0 : c_T.cosgr[lat];
+                if (d.kcos == 1) {  // 59 of the 77 fields: no 1/cos(lat) factor, no multiply per grid point
 #pragma unroll 1
-                for (int k = 2 * wq; k < 2 * wq + 2; k++) fftb_B0(xb + 12 * k * 32, StExchK{xb + 12 * k * 32, sc});
+                    for (int k = 2 * wq; k < 2 * wq + 2; k++) fftb_B0(xb + 12 * k * 32, StExch1{xb + 12 * k * 32});
+                } else {
+                    const double sc = c_T.cosgr[lat];
+#pragma unroll 1
+                    for (int k = 2 * wq; k < 2 * wq + 2; k++) fftb_B0(xb + 12 * k * 32, StExchK{xb + 12 * k * 32, sc});
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 m2_sync(P3_GRP0 + 2 * hemi + 1, 128);
                 if (issuer) {
