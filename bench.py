@@ -239,11 +239,14 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    t_out = 0.0
     for k in range(args.steps):
         e = _speedy.parallel_step(s, c)
         d2h += e.nbytes
         if (k + 1) % NSTEPS_DAY == 0 or k == args.steps - 1:
+            t1 = time.perf_counter()
             d2h += daily_output()
+            t_out += time.perf_counter() - t1
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -303,7 +306,8 @@ def run_b200(args):
                    "members": m_total, "members_per_gpu": m_local, "grid": "96x48x8, T30", "steps_per_day": 36,
                    "l2": "state (11.7 MiB/member) + scratch far exceed the 126 MB L2: no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(s.nbytes + c.nbytes),
-                "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": 1e3 * t_e2e / args.steps},
+                "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "daily_output_ms": 1e3 * t_out},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
