@@ -146,14 +146,15 @@ __device__ __forceinline__ void s2g2_F(const Ctx &c, const InvDesc *__restrict__
                 fftb_A5(ld, xb);
             }
             m2_arrive(M2_EMPTY0 + sl, 512);
-            // the bulk store of the previous quad (other exchange buffer) must have read its buffer before any warp of
-            // the group starts stage A of the next quad: the issuer checks before it joins this barrier
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             m2_sync(M2_GRP0 + 2 * hemi, 128);
             const double sc = d.kcos == 1 ? 1.0 : c_T.cosgr[lat];
 #pragma unroll 1
             for (int k = 2 * wq; k < 2 * wq + 2; k++) fftb_B0(xb + 12 * k * 32, StExchK{xb + 12 * k * 32, sc});
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // the bulk store of the previous quad (other exchange buffer) must have read its buffer before any warp of
+            // the group starts stage A of the NEXT quad, i.e. before anyone leaves the barrier below; by now that store has
+            // had a whole pass to drain, so the issuing warp does not hold up the group (it did when it waited before stage B)
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             m2_sync(M2_GRP0 + 2 * hemi + 1, 128);
             if (issuer && !(M2_EXP & 4)) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(xbuf);
@@ -454,7 +455,8 @@ __device__ __forceinline__ void g2s2_F(const Ctx &c, const FwdDesc *__restrict__
                 } else if (fw == 5) {
                     fftf_B5(ba, st);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // no proxy fence here: stage B only READS the ring entry (the next tensor load into it is requested after the
+                // next 256-thread barrier) and writes the slot, which the async proxy never touches
                 if (hemi == 1) m2_arrive(G2_FULL0 + sl, 512);
             }
         }

@@ -183,7 +183,6 @@ __device__ __forceinline__ void s2g3_F(const Ctx &c, const InvDesc *__restrict__
                     fftb_A5(ld, xb);
                 }
                 if (half == 1) m2_arrive(P3_EMPTY0 + sl, 512);  // this warp has read its share of the slot completely
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 m2_sync(P3_GRP0 + 2 * hemi, 128);
                 if (d.kcos == 1) {  // 59 of the 77 fields: no 1/cos(lat) factor, no multiply per grid point
 #pragma unroll 1
@@ -194,6 +193,10 @@ __device__ __forceinline__ void s2g3_F(const Ctx &c, const InvDesc *__restrict__
                     for (int k = 2 * wq; k < 2 * wq + 2; k++) fftb_B0(xb + 12 * k * 32, StExchK{xb + 12 * k * 32, sc});
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the previous pass's tensor store must have read its exchange buffer before the NEXT pass's stage A writes
+                // it again, i.e. before anyone leaves the barrier below; waiting here (not before stage B, where the
+                // store had only the length of stage A to drain) keeps the issuing warp off the critical path
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 m2_sync(P3_GRP0 + 2 * hemi + 1, 128);
                 if (issuer) {
                     const unsigned sa = (unsigned)__cvta_generic_to_shared(xbuf);
