@@ -767,6 +767,18 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     }
     std::map<int, int> tile_pos;
     for (int t = 0; t < nt; t++) tile_pos[E.cached_tiles[t]] = t;
+    std::vector<int> epos(run.size());  // position of each member's error code in the read-back buffer
+    std::vector<Control *> ctl(run.size());
+    for (size_t q = 0; q < run.size(); q++) {
+        const Member *m = member_of(run[q]);
+        epos[q] = tile_pos[m->tile] * TILE + m->lane;
+        ctl[q] = control_of(cs[idx[q]]);
+    }
+    struct SavedDate {
+        Datetime d;
+        int month_idx;
+    };
+    std::vector<SavedDate> saved(per_step_sync ? run.size() : 0);
     CK(cudaEventRecord(E.ev0, E.stream));
     for (int s = 0; s < nsteps; s++) {
         bool any_daily = false;
@@ -776,20 +788,32 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         }
         for (size_t q = 0; q < run.size(); q++) member_of(run[q])->current_step += 1;
         const bool last = (s == nsteps - 1);
-        if (per_step_sync || last || ((s + 1) % NSTEPS == 0)) {
+        const bool readback = per_step_sync || last || ((s + 1) % NSTEPS == 0);
+        // host mirror of the calendar (the device copy is authoritative for the kernels).  In the per-step driver call it
+        // is advanced while the GPU works on the step and taken back for the (rare) members whose check fails: the
+        // reference does not advance the date of a failed step (speedy.f90:62-69)
+        if (per_step_sync) {
+            for (size_t q = 0; q < run.size(); q++) {
+                saved[q] = SavedDate{ctl[q]->model, ctl[q]->month_idx};
+                if (err_out[idx[q]] == 0) advance_host_date(*ctl[q]);
+            }
+        }
+        if (readback) {
             // error codes: read back at most once a day in batched mode (members that failed keep failing:
             // a NaN/blown-up state never passes the check again unless it is NaN, which the reference also lets pass)
             CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
             for (size_t q = 0; q < run.size(); q++) {
-                Member *m = member_of(run[q]);
-                const int code = E.h_err[tile_pos[m->tile] * TILE + m->lane];
-                if (code != 0 && err_out[idx[q]] == 0) err_out[idx[q]] = code;
+                const int code = E.h_err[epos[q]];
+                if (code != 0 && err_out[idx[q]] == 0) {
+                    err_out[idx[q]] = code;
+                    if (per_step_sync) ctl[q]->model = saved[q].d, ctl[q]->month_idx = saved[q].month_idx;
+                }
             }
         }
-        // host mirror of the calendar (the device copy is authoritative for the kernels)
-        for (size_t q = 0; q < run.size(); q++) {
-            if (err_out[idx[q]] == 0) advance_host_date(*control_of(cs[idx[q]]));
+        if (!per_step_sync) {
+            for (size_t q = 0; q < run.size(); q++)
+                if (err_out[idx[q]] == 0) advance_host_date(*ctl[q]);
         }
     }
     CK(cudaEventRecord(E.ev1, E.stream));
