@@ -253,6 +253,9 @@ def run_b200(args):
     e2e_value = m_total * args.steps / NSTEPS_DAY / t_e2e
 
     # ---- roofline of the dominant kernel class (one instrumented step on one 512-member chunk) -----------------
+    # the roofline compares one kernel timed alone with the burst HBM figure of MEASURED_PEAKS.json, so the profiled steps
+    # start from an idle GPU: the two timed regions above leave the chip at its power cap (SM clock down to ~1.8 GHz)
+    time.sleep(2.0)
     n_prof = min(m_local, 512)
     _speedy.profile_step(s[:n_prof], c[:n_prof])
     prof = None  # three consecutive steps = one short-wave step + two long-wave-only steps, averaged
