@@ -164,6 +164,22 @@ __device__ __forceinline__ void raw_update(double *p1, double *p2, double o1, do
     if (act) *p1 = o1, *p2 = o2;
 }
 
+// raw_update with a zero tendency for the coefficients outside the truncation (see k_spec_step_vq).  The two time levels
+// are written only where the filter changed them: they are exact zeros there unless the host stored something else, and
+// zeros stay zeros, so these rows cost their reads only.
+__device__ __forceinline__ void raw_update_idle(double *p1, double *p2, const double a1, const double a2, const double trf,
+                                                const int j1, const double dt, const double eps, const bool act) {
+    double o1 = a1, o2 = a2;
+    const double fdt = 0.0 * trf;
+    const double fnew = o1 + dt * fdt;
+    double oj1 = (j1 == 1) ? o1 : o2;
+    o1 = oj1 + (D_WIL * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (j1 == 1) oj1 = o1;
+    o2 = fnew - ((1.0 - D_WIL) * eps) * ((o1 - 2.0 * oj1) + fnew);
+    if (act && __double_as_longlong(o1) != __double_as_longlong(a1)) *p1 = o1;
+    if (act && __double_as_longlong(o2) != __double_as_longlong(a2)) *p2 = o2;
+}
+
 // Vorticity and tracer: no vertical coupling -> one thread per (coefficient, component, level)
 // (tendencies.f90:238-268 spectral part, time_stepping.f90:78-144)
 __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const ScratchLayout L, const int j1, const double dt,
@@ -179,7 +195,18 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
     const bool act = lane_active(c, t, lane);
     const double *F = scp(c, t, L.sfwd, lane) + e;
     double *vor = stp(c, t, c.off[V_vor], lane) + e + k * lev, *trs = stp(c, t, c.off[V_tr], lane) + e + k * lev;
-    const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q], trf = G->trfilt[q];
+    const double trf = G->trfilt[q];
+    // Outside the triangular truncation (m + n > 30, half of the (31,32) array) step_field multiplies the whole tendency
+    // by trfilt = 0 (time_stepping.f90:177-179, spectral.f90:72-83): those coefficients only go through the time filter
+    // with a zero tendency, so their 8 tendency rows, the correction field and the damping tables are never loaded.
+    const bool live = (m + n <= NTRUNC) || dump >= 0;
+    if (!live) {
+        const double v1 = *vor, q1 = *trs, v2 = vor[tl], q2 = trs[tl];
+        raw_update_idle(vor, vor + tl, v1, v2, trf, j1, dt, eps, act);
+        raw_update_idle(trs, trs + tl, q1, q2, trf, j1, dt, eps, act);
+        return;
+    }
+    const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q];
     double vo, dq, dum;
     vdspec_comp<1>(gx, ym, yp, F + (FW_SU + k) * lev, F + (FW_SV + k) * lev, n, cc, vo, dum);
     vdspec_comp<2>(gx, ym, yp, F + (FW_UQ + k) * lev, F + (FW_VQ + k) * lev, n, cc, dum, dq);
@@ -218,6 +245,22 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
            *ps = stp(c, t, c.off[V_ps], lane) + e;
     const double *phi = stp(c, t, c.off[V_phi], lane) + e;
     const double el2 = G->el2[q], trf = G->trfilt[q];
+    if (m + n > NTRUNC && dump < 0) {  // outside the truncation: zero tendency, time filter only (see k_spec_step_vq)
+        double a1[2 * KX + 1], a2[2 * KX + 1];
+#pragma unroll
+        for (int k = 0; k < KX; k++) {
+            a1[k] = dvs[k * lev], a2[k] = dvs[tl + k * lev];
+            a1[KX + k] = tt[k * lev], a2[KX + k] = tt[tl + k * lev];
+        }
+        a1[2 * KX] = ps[0], a2[2 * KX] = ps[lev];
+        raw_update_idle(ps, ps + lev, a1[2 * KX], a2[2 * KX], trf, j1, dt, eps, act);
+#pragma unroll
+        for (int k = 0; k < KX; k++) {
+            raw_update_idle(dvs + k * lev, dvs + tl + k * lev, a1[k], a2[k], trf, j1, dt, eps, act);
+            raw_update_idle(tt + k * lev, tt + tl + k * lev, a1[KX + k], a2[KX + k], trf, j1, dt, eps, act);
+        }
+        return;
+    }
     const double gx = G->gradx[m], ym = G->vddym[q], yp = G->vddyp[q];
     // rows needed only after the (long) implicit solve: start pulling them into L2 now
     if (dump < 0) {

@@ -600,9 +600,11 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     const long long tl2 = (long long)(j2 - 1) * NSP * KX;
     // spectral pre-operators: geopotential (time level 1), uvspec, grad(ps)
     launch_geopotential(E.stream, c, E.off[V_t], E.off[V_phis], E.off[V_phi]);
-    launch_uvspec(E.stream, c, E.off[V_vor] + tl2, E.off[V_div] + tl2, REF_SCR | L.ucos, REF_SCR | L.vcos, KX);
-    launch_uvspec(E.stream, c, E.off[V_vor] + 7ll * NSP, E.off[V_div] + 7ll * NSP, REF_SCR | L.ucosp8, REF_SCR | L.vcosp8, 1);
-    launch_gradient(E.stream, c, E.off[V_ps] + (long long)(j2 - 1) * NSP, REF_SCR | L.dpx, REF_SCR | L.dpy);
+    // k_spec2grid_mma3 reads the rows inside the nsh2 mask only: the pre-operators skip the other 47 % of each field
+    const int tri = fused_mode() >= 7 ? 1 : 0;
+    launch_uvspec(E.stream, c, E.off[V_vor] + tl2, E.off[V_div] + tl2, REF_SCR | L.ucos, REF_SCR | L.vcos, KX, tri);
+    launch_uvspec(E.stream, c, E.off[V_vor] + 7ll * NSP, E.off[V_div] + 7ll * NSP, REF_SCR | L.ucosp8, REF_SCR | L.vcosp8, 1, tri);
+    launch_gradient(E.stream, c, E.off[V_ps] + (long long)(j2 - 1) * NSP, REF_SCR | L.dpx, REF_SCR | L.dpy, tri);
     COUNT(4);
     prof_mark(E.stream, PC_PREOPS);
     run_inverse(c, E.d_inv[j2 - 1], 77);
@@ -887,7 +889,7 @@ static void s2g_member(Member &m) {  // prognostics.f90:125-154
 }
 static void s2g_ctx(const Ctx &c) {
     const ScratchLayout &L = E.L;
-    launch_uvspec(E.stream, c, E.off[V_vor], E.off[V_div], REF_SCR | L.ucos, REF_SCR | L.vcos, KX);
+    launch_uvspec(E.stream, c, E.off[V_vor], E.off[V_div], REF_SCR | L.ucos, REF_SCR | L.vcos, KX, 0);
     COUNT(1);
     std::vector<InvDesc> v;
     for (int k = 0; k < KX; k++) {

@@ -30,8 +30,8 @@ void launch_legendre_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf,
 void launch_fft_inv(cudaStream_t s, const Ctx &c, const InvDesc *d, int nf, long long four_off);
 void launch_fft_fwd(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, int nf, long long four_off);
 void launch_legendre_dir(cudaStream_t s, const Ctx &c, const FwdOut *o, int nf, long long four_off);
-void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev);
-void launch_gradient(cudaStream_t s, const Ctx &c, FieldRef psi, FieldRef dx, FieldRef dy);
+void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev, int tri);
+void launch_gradient(cudaStream_t s, const Ctx &c, FieldRef psi, FieldRef dx, FieldRef dy, int tri);
 void launch_geopotential(cudaStream_t s, const Ctx &c, FieldRef tlev, FieldRef phis, FieldRef phi);
 
 }  // namespace spdy

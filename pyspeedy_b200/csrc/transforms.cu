@@ -339,10 +339,14 @@ __device__ __forceinline__ void uvspec_elem(const GlobTables *G, const double *v
     }
 }
 
-__global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev) {
+// tri: the consumer is an inverse transform that reads the rows n <= 31 - m only (legendre.f90:143-158 through nsh2;
+// k_spec2grid_mma3 never touches the others), so the 465 coefficients beyond them are neither loaded nor stored
+__global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev,
+                                                int tri) {
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     if (q >= NSPC) return;
     const int m = q % MX, n = q / MX;
+    if (tri && m + n > NTRUNC + 1) return;
     const double *pv = refp(c, t, vor, lane), *pd = refp(c, t, dv, lane);
     double *pu = refp(c, t, u, lane), *pw = refp(c, t, v, lane);
     for (int k = 0; k < nlev; k++)
@@ -351,10 +355,11 @@ __global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, Field
 }
 
 // gradient (spectral.f90:275-296)
-__global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, FieldRef dx, FieldRef dy) {
+__global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, FieldRef dx, FieldRef dy, int tri) {
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     if (q >= NSPC) return;
     const int m = q % MX, n = q / MX;
+    if (tri && m + n > NTRUNC + 1) return;  // see k_uvspec
     const GlobTables *G = c.G;
     const double *p = refp(c, t, psi, lane);
     double *px = refp(c, t, dx, lane), *py = refp(c, t, dy, lane);
@@ -441,11 +446,11 @@ void launch_legendre_dir(cudaStream_t s, const Ctx &c, const FwdOut *o, int nf, 
     if (!nf) return;
     k_legendre_dir<<<dim3(nf * 16, c.ntiles), 128, 0, s>>>(c, o, four_off);
 }
-void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev) {
-    k_uvspec<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, vor, dv, u, v, nlev);
+void launch_uvspec(cudaStream_t s, const Ctx &c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev, int tri) {
+    k_uvspec<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, vor, dv, u, v, nlev, tri);
 }
-void launch_gradient(cudaStream_t s, const Ctx &c, FieldRef psi, FieldRef dx, FieldRef dy) {
-    k_gradient<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, psi, dx, dy);
+void launch_gradient(cudaStream_t s, const Ctx &c, FieldRef psi, FieldRef dx, FieldRef dy, int tri) {
+    k_gradient<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, psi, dx, dy, tri);
 }
 void launch_geopotential(cudaStream_t s, const Ctx &c, FieldRef tlev, FieldRef phis, FieldRef phi) {
     k_geopotential<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, tlev, phis, phi);
