@@ -49,8 +49,11 @@ ALG_BYTES = {
     "grid_dyn": 4608 * (50 + 33) * 8,
     # 158 doubles per column on a long-wave-only step, 167 on a short-wave step (every 3rd): average of 3 steps
     "physics": 4608 * (2 * 158 + 167) * 8 // 3,
-    "spec_step": (73 + 8 + 2 * 33 + 2 * 33 + 2) * SPEC_B,
+    # 496 coefficients inside the triangular truncation: 73 forward outputs + 8 phi + 2 x 33 state rows + 2 correction rows
+    # read, 2 x 33 state rows written; the 496 outside it: their 2 x 33 state rows read (zero tendency, stored only if changed)
+    "spec_step": 496 * 16 * ((73 + 8 + 2 * 33 + 2 + 2 * 33) + 2 * 33),
 }
+SPEC_MASK_B = 527 * 16  # rows n <= 31 - m of a spectral field: what the fused forward kernel writes for the spectral step
 
 
 def measured_peaks():
@@ -268,7 +271,7 @@ def run_b200(args):
     if prof["legendre_inv"] == 0.0:  # default path: spec -> grid is ONE fused kernel, the Fourier array stays on chip
         alg["fft_inv"], alg["legendre_inv"] = 77 * (SPEC_B + GRID_B), 0
     if prof["legendre_dir"] == 0.0:  # default path: grid -> spec is one fused kernel per loader mode as well
-        alg["fft_fwd"], alg["legendre_dir"] = (33 + 64) * GRID_B + 73 * SPEC_B, 0
+        alg["fft_fwd"], alg["legendre_dir"] = (33 + 64) * GRID_B + 73 * SPEC_MASK_B, 0
     cls = max(alg, key=lambda k: prof[k])
     achieved = alg[cls] * n_prof / (prof[cls] * 1e-3) / 1e9
     total_prof = sum(prof.values())

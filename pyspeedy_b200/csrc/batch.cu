@@ -138,7 +138,7 @@ int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
     if (fused_mode() >= 6) {  // the model step's default forward kernel (the workspace is a scratch arena)
-        launch_grid2spec_mma2(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
+        launch_grid2spec_mma2(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1, 0);
     } else if (use_fused()) {
         launch_grid2spec_fused(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
     } else {

@@ -511,16 +511,18 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     prof_mark(E.stream, PC_FFT_INV);
     COUNT(2);
 }
-static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout) {
+// sparse: the outputs feed the model's spectral step, which reads the rows inside the nsh2 mask only
+static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout,
+                              int sparse = 0) {
     if (fused_mode() >= 7 && lists == E.d_fwd) {  // the step's 73 fields in ONE launch of the fused forward kernel
-        launch_grid2spec_mma2(E.stream, c, FM_ALL, E.d_fwd_all, outs, E.n_fwd_all);
+        launch_grid2spec_mma2(E.stream, c, FM_ALL, E.d_fwd_all, outs, E.n_fwd_all, sparse);
         COUNT(1);
         prof_mark(E.stream, PC_FFT_FWD);
         return;
     }
     if (fused_mode() >= 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
         for (int m = 0; m < FM_NMODES; m++)
-            if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
+            if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m], 0), COUNT(1);
         prof_mark(E.stream, PC_FFT_FWD);
         return;
     }
@@ -620,7 +622,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
         prof_mark(E.stream, PC_PHYSICS);
         COUNT(2);
     }
-    run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT);
+    run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT, dump < 0 ? 1 : 0);  // the tendency dump reads every row
     launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx, dump);
     prof_mark(E.stream, PC_SPEC_STEP);
     COUNT(2);  // k_spec_step_vq + k_spec_step_dt

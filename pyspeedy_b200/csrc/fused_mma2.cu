@@ -306,12 +306,16 @@ __device__ __forceinline__ void md2_mma(MdC2<M> &c, const double *__restrict__ A
     }
 }
 //   Xl : spectral output + lane offset (row 2 * (L/4) of a parity, members 2*(L%4), +1); all 32 rows n are written
-template <int M> __device__ __forceinline__ void md2_store(const MdC2<M> &c, double *__restrict__ Xl) {
+//   sparse: the consumer reads the rows inside the nsh2 mask only (the model's spectral step: coefficients with
+//   m + n <= 30 and their n +- 1 neighbours), so the exact zeros of the other rows (47 % of the field) are not written
+template <int M>
+__device__ __forceinline__ void md2_store(const MdC2<M> &c, double *__restrict__ Xl, const int col, const int sparse) {
     constexpr int NE = MD2_NE(M), NO = MD2_NO(M);
 #pragma unroll
     for (int par = 0; par < 2; par++)
 #pragma unroll
         for (int i = 0; i < 2; i++) {
+            if (sparse && par + 2 * col + 16 * i > 31 - M) continue;  // vdspec reads n + 1 <= 31 - m (row (0,31) is a zero)
             double2 *pr = reinterpret_cast<double2 *>(Xl + (size_t)((2 * M) + M2 * (par + 16 * i)) * TILE);
             double2 *pi = reinterpret_cast<double2 *>(Xl + (size_t)((2 * M + 1) + M2 * (par + 16 * i)) * TILE);
             const bool have = i < (par ? NO : NE);
@@ -324,7 +328,7 @@ template <int M> __device__ __forceinline__ void md2_store(const MdC2<M> &c, dou
 
 template <int LW>
 __device__ __forceinline__ void g2s2_L(const Ctx &c, const FwdDesc *__restrict__ descs, const FwdOut *__restrict__ outs,
-                                       const int nwork, const double *slots, const int lane) {
+                                       const int nwork, const double *slots, const int lane, const int sparse) {
     constexpr int M3 = (LW != 7) ? 22 - LW : 15;
     const int kk = lane & 3, col = lane >> 2;
     const double *pq = c.G->pq_dir2 + lane;
@@ -347,8 +351,8 @@ __device__ __forceinline__ void g2s2_L(const Ctx &c, const FwdDesc *__restrict__
             m2_arrive(G2_EMPTY0 + sl, 512);
         }
         double *Xl = refp(c, t, outs[descs[f].fidx].dst, 0) + (size_t)(M2 * 2 * col) * TILE + MQ_NM * grp + 2 * kk;
-        md2_store(c0, Xl), md2_store(c1, Xl), md2_store(c2, Xl);
-        if (LW != 7) md2_store(c3, Xl);
+        md2_store(c0, Xl, col, sparse), md2_store(c1, Xl, col, sparse), md2_store(c2, Xl, col, sparse);
+        if (LW != 7) md2_store(c3, Xl, col, sparse);
     }
 }
 
@@ -466,7 +470,7 @@ __device__ __forceinline__ void g2s2_F(const Ctx &c, const FwdDesc *__restrict__
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) k_grid2spec_mma2(const Ctx c, const FwdDesc *__restrict__ descs,
                                                            const FwdOut *__restrict__ outs, int nwork,
-                                                           const __grid_constant__ CUtensorMap tmap) {
+                                                           const __grid_constant__ CUtensorMap tmap, int sparse) {
     extern __shared__ __align__(128) double g2_sm[];
     constexpr int G2_NB = G2Cfg<MODE>::NB;
     double *bufs = g2_sm, *slots = g2_sm + (size_t)G2_NB * G2Cfg<MODE>::NOP * M2_XH;
@@ -476,19 +480,20 @@ __global__ void __launch_bounds__(512, 1) k_grid2spec_mma2(const Ctx c, const Fw
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     switch (warp) {
-        case 0: g2s2_L<0>(c, descs, outs, nwork, slots, lane); break;
-        case 1: g2s2_L<1>(c, descs, outs, nwork, slots, lane); break;
-        case 2: g2s2_L<2>(c, descs, outs, nwork, slots, lane); break;
-        case 3: g2s2_L<3>(c, descs, outs, nwork, slots, lane); break;
-        case 4: g2s2_L<4>(c, descs, outs, nwork, slots, lane); break;
-        case 5: g2s2_L<5>(c, descs, outs, nwork, slots, lane); break;
-        case 6: g2s2_L<6>(c, descs, outs, nwork, slots, lane); break;
-        case 7: g2s2_L<7>(c, descs, outs, nwork, slots, lane); break;
+        case 0: g2s2_L<0>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 1: g2s2_L<1>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 2: g2s2_L<2>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 3: g2s2_L<3>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 4: g2s2_L<4>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 5: g2s2_L<5>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 6: g2s2_L<6>(c, descs, outs, nwork, slots, lane, sparse); break;
+        case 7: g2s2_L<7>(c, descs, outs, nwork, slots, lane, sparse); break;
         default: g2s2_F<MODE>(c, descs, nwork, slots, bufs, mbar0, &tmap, warp - 8, lane); break;
     }
 }
 
-template <int MODE> static void launch_g2s2_mode(cudaStream_t s, const Ctx &c, const FwdDesc *d, const FwdOut *o, int nf) {
+template <int MODE>
+static void launch_g2s2_mode(cudaStream_t s, const Ctx &c, const FwdDesc *d, const FwdOut *o, int nf, int sparse) {
     static int sms = 0;
     constexpr size_t SMEM = G2Cfg<MODE>::SMEM;
     static_assert(SMEM <= 232448, "shared memory per CTA on sm_100a");
@@ -502,18 +507,18 @@ template <int MODE> static void launch_g2s2_mode(cudaStream_t s, const Ctx &c, c
         }
     }
     const int nwork = nf * c.ntiles * (TILE / MQ_NM);
-    k_grid2spec_mma2<MODE><<<nwork < sms ? nwork : sms, 512, SMEM, s>>>(c, d, o, nwork, s2g2_tensor_map(c));
+    k_grid2spec_mma2<MODE><<<nwork < sms ? nwork : sms, 512, SMEM, s>>>(c, d, o, nwork, s2g2_tensor_map(c), sparse);
 }
 // all operand fields must live in the scratch arena (true for the model step's lists)
-void launch_grid2spec_mma2(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, const FwdOut *o, int nf) {
+void launch_grid2spec_mma2(cudaStream_t s, const Ctx &c, int mode, const FwdDesc *d, const FwdOut *o, int nf, int sparse) {
     if (!nf) return;
     switch (mode) {
-        case FM_ALL: launch_g2s2_mode<FM_ALL>(s, c, d, o, nf); break;  // mixed list, FwdDesc::mode per field
-        case FM_PLAIN: launch_g2s2_mode<FM_PLAIN>(s, c, d, o, nf); break;
-        case FM_COS: launch_g2s2_mode<FM_COS>(s, c, d, o, nf); break;
-        case FM_KE: launch_g2s2_mode<FM_KE>(s, c, d, o, nf); break;
-        case FM_FLUXT: launch_g2s2_mode<FM_FLUXT>(s, c, d, o, nf); break;
-        default: launch_g2s2_mode<FM_FLUX>(s, c, d, o, nf); break;
+        case FM_ALL: launch_g2s2_mode<FM_ALL>(s, c, d, o, nf, sparse); break;  // mixed list, FwdDesc::mode per field
+        case FM_PLAIN: launch_g2s2_mode<FM_PLAIN>(s, c, d, o, nf, sparse); break;
+        case FM_COS: launch_g2s2_mode<FM_COS>(s, c, d, o, nf, sparse); break;
+        case FM_KE: launch_g2s2_mode<FM_KE>(s, c, d, o, nf, sparse); break;
+        case FM_FLUXT: launch_g2s2_mode<FM_FLUXT>(s, c, d, o, nf, sparse); break;
+        default: launch_g2s2_mode<FM_FLUX>(s, c, d, o, nf, sparse); break;
     }
 }
 
