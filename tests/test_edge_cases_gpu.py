@@ -138,3 +138,41 @@ def test_sst_anomaly_across_month_boundary(oracle):
             for v in checks:
                 assert relerr(m[v], st[v]) < 1e-8, (step, v, relerr(m[v], st[v]))
     assert _speedy.get_model_datetime(m._state_cnt) == tuple(ctl.date) == (1982, 2, 1, 18, 40)
+
+
+def test_coefficients_outside_the_truncation(oracle):
+    """step_field truncates the TENDENCY (trfilt, time_stepping.f90:177-179), not the state: coefficients with
+    m + n > 30 that the host stored (or that grid2spectral left in row m + n = 31) keep going through the Robert-Asselin-
+    Williams filter with a zero tendency, and row m + n = 31 still enters the inverse transforms and the n +- 1 stencils.
+    The CUDA spectral step does not evaluate tendencies there, stores those rows only where the filter changed them, and
+    the forward transform / vort2vel skip the rows nobody reads: all of that must be invisible."""
+    from pyspeedy_b200 import Speedy, _speedy
+
+    st, ctl = _oracle_member(oracle, (1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
+    m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    m.set_bc()
+    for _ in range(2):  # leave the rest state first
+        assert st.step(ctl) == 0
+        assert _speedy.step(m._state_cnt, m._control_cnt) == 0
+    mm, nn = np.meshgrid(np.arange(31), np.arange(32), indexing="ij")
+    outside = (mm + nn) > 30
+    rng = np.random.default_rng(5)
+    for v, amp in (("t", 1e-3), ("vor", 1e-9), ("div", 1e-9), ("tr", 1e-7), ("ps", 1e-6)):
+        x = np.array(st[v])
+        assert x.shape[:2] == (31, 32)
+        noise = amp * (rng.standard_normal(x.shape) + 1j * rng.standard_normal(x.shape))
+        x = x + noise * outside.reshape((31, 32) + (1,) * (x.ndim - 2))
+        st[v] = x
+        m[v] = x
+    for step in range(5):
+        assert st.step(ctl) == 0
+        assert _speedy.step(m._state_cnt, m._control_cnt) == 0
+        for v in PROG:
+            a, b = np.asarray(m[v]), np.asarray(st[v])
+            assert relerr(a, b) < 1e-11, (step, v, relerr(a, b))
+            assert np.abs(b[outside]).max() > 0  # the stored values are still there, filtered
+            assert relerr(a[outside], b[outside]) < 1e-11, (step, v, "outside", relerr(a[outside], b[outside]))
+    m.spectral2grid()
+    st.spectral2grid()
+    for v in ("u_grid", "v_grid", "t_grid", "q_grid", "phi_grid", "ps_grid"):
+        assert relerr(m[v], st[v]) < 1e-10, (v, relerr(m[v], st[v]))
