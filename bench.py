@@ -196,23 +196,37 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    out_buf = {}
+
     def daily_output():
-        """spectral2grid of every member + ensemble mean/spread of the default outputs; returns D2H bytes."""
+        """spectral2grid of every member + ensemble mean/spread of the default outputs; returns D2H bytes.
+        The per-variable sums (reduced over this rank's members by the library) are gathered in one device buffer: one
+        NCCL all-reduce and one device-to-host copy per simulated day."""
         _speedy.batch_spectral2grid(s)
-        nbytes = 0
+        parts, off = [], 0
         for v in DEFAULT_OUTPUT_VARS:
             e = _driver.REGISTRY[_driver.VAR_ID[v]]
             dev, ne = C.c_void_p(), C.c_size_t()
             lib.spdy_ensemble_sums_device(_driver._ptr(s), len(s), e["id"], None, C.byref(dev), C.byref(ne))
-            t = torch.as_tensor(CudaArray(dev.value, 2 * ne.value), device="cuda")
-            if world > 1:
-                dist.all_reduce(t)
-            host = t.cpu().numpy()
-            mean = host[: ne.value] / m_total
-            spread = np.sqrt(np.maximum(host[ne.value:] / m_total - mean * mean, 0.0))
-            nbytes += host.nbytes
+            n2 = 2 * ne.value
+            if "t" not in out_buf or out_buf["t"].numel() < off + n2:
+                grown = torch.empty(max(off + n2, 2 * 2 * 5 * 96 * 48 * 8 + 2 * 96 * 48), dtype=torch.float64, device="cuda")
+                if "t" in out_buf:
+                    grown[:off].copy_(out_buf["t"][:off])
+                out_buf["t"] = grown
+            out_buf["t"][off:off + n2].copy_(torch.as_tensor(CudaArray(dev.value, n2), device="cuda"))
+            torch.cuda.current_stream().synchronize()  # the library reuses its sum buffer for the next variable
+            parts.append((off, ne.value))
+            off += n2
+        t = out_buf["t"][:off]
+        if world > 1:
+            dist.all_reduce(t)
+        host = t.cpu().numpy()
+        for o, n in parts:
+            mean = host[o:o + n] / m_total
+            spread = np.sqrt(np.maximum(host[o + n:o + 2 * n] / m_total - mean * mean, 0.0))
             del mean, spread
-        return nbytes
+        return host.nbytes
 
     # ---- warm-up, then the device-resident timed region --------------------------------------------------------
     err = _speedy.run_steps(s, c, max(args.warmup, 3))

@@ -455,10 +455,11 @@ __global__ void __launch_bounds__(256) k_ens_reduce(const double *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
-// SPDY_FUSED selects the transform kernels: 3 (default) = spec -> grid through the fused DMMA kernel of
-// fused_mma.cu, grid -> spec through the separate FFT and Legendre kernels; 0 = separate kernels both ways;
-// 1 = the first-generation fused kernels of fused.cu both ways, 2 = fused.cu for spec -> grid only.
-// See DESIGN.md section 4 for the measurements behind the default.
+// SPDY_FUSED selects the transform kernels: 7 (default) = spec -> grid through k_spec2grid_mma3 (fused_mma3.cu),
+// grid -> spec through ONE mixed-mode launch of k_grid2spec_mma2 (fused_mma2.cu); 6 / 5 = second-generation DMMA + TMA
+// kernels both ways / spec -> grid only; 4 / 3 = first DMMA kernels (fused_mma.cu) both ways / spec -> grid only;
+// 0 = separate FFT and Legendre kernels both ways; 1 = the first-generation fused kernels of fused.cu both ways,
+// 2 = fused.cu for spec -> grid only.  See DESIGN.md sections 4 and 8 for the measurements behind the default.
 static int fused_mode() {
     static int v = -1;
     if (v < 0) {
