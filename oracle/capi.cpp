@@ -9,8 +9,9 @@
 using namespace orc;
 
 namespace {
+State *g_tables = nullptr;
 State &tables() {  // module tables only (geometry, spectral, implicit with the leapfrog time step 2*delt)
-    static State *t = nullptr;
+    State *&t = g_tables;
     if (!t) {
         t = new State();
         t->geo.initialize();
@@ -26,6 +27,13 @@ size_t var_count(const State &s, int v) { return s.var[v].size(); }
 }  // namespace
 
 extern "C" {
+
+// diagnostic switches of speedy_oracle.hpp (Diag); the shared tables are rebuilt on the next use
+void orc_set_diag(int exact_fft, int exact_nodes) {
+    g_diag.exact_fft = exact_fft != 0, g_diag.exact_nodes = exact_nodes != 0;
+    delete g_tables;
+    g_tables = nullptr;
+}
 
 void *orc_state_create() { return new State(); }
 void *orc_state_clone(void *p) {

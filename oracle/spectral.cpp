@@ -4,6 +4,29 @@
 
 namespace orc {
 
+Diag g_diag;
+// FFTPACK constants: the reference's REAL(4)-valued ones, or exact doubles under the diagnostic switch
+static inline double k_tpi() { return g_diag.exact_fft ? 8.0 * atan(1.0) : 8.0 * F_ATAN1; }
+static inline double k_taui() { return g_diag.exact_fft ? 0.5 * sqrt(3.0) : 0.5 * F_SQRT3; }
+static inline double k_sqrt2() { return g_diag.exact_fft ? sqrt(2.0) : F_SQRT2; }
+// Gaussian node i (1 = nearest the pole) by the Newton iteration of legendre.f90:224-257 (diagnostic switch only)
+static double gauss_node(int i) {
+    const int n = 2 * iy;
+    double z = cos(3.14159265358979323846 * ((double)i - 0.25) / ((double)n + 0.5)), z1 = 2.0;
+    for (int it = 0; it < 100 && fabs(z - z1) > 2.220446049250313e-16; it++) {
+        double p1 = 1.0, p2 = 0.0;
+        for (int j = 1; j <= n; j++) {
+            double p3 = p2;
+            p2 = p1;
+            p1 = ((2.0 * (double)j - 1.0) * z * p2 - ((double)j - 1.0) * p3) / j;
+        }
+        const double pp = (double)n * (z * p1 - p2) / (z * z - 1.0);
+        z1 = z;
+        z = z1 - p1 / pp;
+    }
+    return z;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // geometry.f90:61-156
 void Geometry::initialize() {
@@ -21,7 +44,7 @@ void Geometry::initialize() {
     for (int j = 1; j <= iy; j++) {  // :108-118 -- the argument and the cosine are REAL(4)
         int jj = il + 1 - j;
         float arg = 3.141592654f * ((float)j - 0.25f) / ((float)il + 0.5f);
-        sia_half[j] = (double)cosf(arg);
+        sia_half[j] = g_diag.exact_nodes ? gauss_node(j) : (double)cosf(arg);
         coa_half[j] = sqrt(1.0 - sia_half[j] * sia_half[j]);
         sia[j] = -sia_half[j];
         sia[jj] = sia_half[j];
@@ -82,7 +105,7 @@ void rffti1(int n, double *wa, int *ifac) {
     }
     ifac[1] = n;
     ifac[2] = nf;
-    const double tpi = 8.0 * F_ATAN1;  // :39  tpi = 8.*atan(1.) in REAL(4): 8*0.785398185f is exact in float
+    const double tpi = k_tpi();  // :39  tpi = 8.*atan(1.) in REAL(4): 8*0.785398185f is exact in float
     const double argh = tpi / n;
     int is = 0, l1 = 1;
     if (nf - 1 == 0) return;
@@ -142,7 +165,7 @@ static void radb2(int ido, int l1, const double *cc, double *ch, const double *w
 // fftpack.f90:256-326
 static void radb3(int ido, int l1, const double *cc, double *ch, const double *wa1, const double *wa2) {
     const int ip_ = 3;
-    const double taur = -0.5, taui = 0.5 * F_SQRT3;  // :268-269 REAL(4) expression .5*sqrt(3.)
+    const double taur = -0.5, taui = k_taui();  // :268-269 REAL(4) expression .5*sqrt(3.)
     for (int k = 1; k <= l1; k++) {
         double tr2 = CCB(ido, 2, k) + CCB(ido, 2, k);
         double cr2 = CCB(1, 1, k) + taur * tr2;
@@ -176,7 +199,7 @@ static void radb3(int ido, int l1, const double *cc, double *ch, const double *w
 static void radb4(int ido, int l1, const double *cc, double *ch, const double *wa1, const double *wa2,
                   const double *wa3) {
     const int ip_ = 4;
-    const double sqrt2 = F_SQRT2;  // :341 sqrt(2.) REAL(4)
+    const double sqrt2 = k_sqrt2();  // :341 sqrt(2.) REAL(4)
     for (int k = 1; k <= l1; k++) {
         double tr1 = CCB(1, 1, k) - CCB(ido, 4, k);
         double tr2 = CCB(1, 1, k) + CCB(ido, 4, k);
@@ -258,7 +281,7 @@ static void radf2(int ido, int l1, const double *cc, double *ch, const double *w
 // fftpack.f90:774-842
 static void radf3(int ido, int l1, const double *cc, double *ch, const double *wa1, const double *wa2) {
     const int ip_ = 3;
-    const double taur = -0.5, taui = 0.5 * F_SQRT3;
+    const double taur = -0.5, taui = k_taui();
     for (int k = 1; k <= l1; k++) {
         double cr2 = CCF(1, k, 2) + CCF(1, k, 3);
         CHF(1, 1, k) = CCF(1, k, 1) + cr2;
@@ -292,7 +315,7 @@ static void radf3(int ido, int l1, const double *cc, double *ch, const double *w
 static void radf4(int ido, int l1, const double *cc, double *ch, const double *wa1, const double *wa2,
                   const double *wa3) {
     const int ip_ = 4;
-    const double hsqt2 = 0.5 * F_SQRT2;  // :857 .5*sqrt(2.) REAL(4) (exact halving)
+    const double hsqt2 = 0.5 * k_sqrt2();  // :857 .5*sqrt(2.) REAL(4) (exact halving)
     for (int k = 1; k <= l1; k++) {
         double tr1 = CCF(1, k, 2) + CCF(1, k, 4);
         double tr2 = CCF(1, k, 1) + CCF(1, k, 3);
@@ -414,8 +437,9 @@ void Spectral::legendre_poly(int j, double *poly) const {
     auto REP = [&](int m, int n) { return repsi[(m - 1) + (size_t)(mx + 1) * (n - 1)]; };
     double y = geo->coa_half[j], x = geo->sia_half[j];
     for (int m = 1; m <= mx; m++)  // :277 all REAL(4), sqrtf
-        consq[m] = (double)sqrtf(0.5f * (2.0f * (float)m + 1.0f) / (float)m);
-    ALP(1, 1) = F_SQRTH;  // :281 sqrt(0.5) folded REAL(4)
+        consq[m] = g_diag.exact_nodes ? sqrt(0.5 * (2.0 * m + 1.0) / m)
+                                      : (double)sqrtf(0.5f * (2.0f * (float)m + 1.0f) / (float)m);
+    ALP(1, 1) = g_diag.exact_nodes ? sqrt(0.5) : F_SQRTH;  // :281 sqrt(0.5) folded REAL(4)
     for (int m = 2; m <= mx + 1; m++) ALP(m, 1) = consq[m - 1] * y * ALP(m - 1, 1);
     for (int m = 1; m <= mx + 1; m++) ALP(m, 2) = (x * ALP(m, 1)) * REP(m, 2);
     for (int n = 3; n <= nx; n++)

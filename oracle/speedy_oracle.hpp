@@ -50,6 +50,16 @@ const double thd = FL(2.4), thdd = FL(2.4), thds = FL(12.0), tdrs = (double)(24.
 // mod_radcon.f90:11-16
 const double albsea = FL(0.07), albice = FL(0.60), albsn = FL(0.60), epslw = FL(0.05), emisfc = FL(0.98);
 
+// DIAGNOSTIC SWITCHES (default off; tests/test_oracle_transcription.py only).  They replace reference *constants* by
+// their exact values so that the transcription of the *algorithm* can be checked against mathematics the reference
+// itself cannot satisfy: with exact_fft the FFTPACK passes must equal the DFT to rounding; with
+// exact_nodes (true Gaussian latitudes instead of the REAL(4) Newton start value of geometry.f90:110) the Legendre
+// pair must be an exact quadrature.  Tables built while a switch is on are not the reference's.
+struct Diag {
+    bool exact_fft = false, exact_nodes = false;
+};
+extern Diag g_diag;
+
 struct cplx {
     double re, im;
 };

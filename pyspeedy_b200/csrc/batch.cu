@@ -118,14 +118,8 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
     Ctx c = ws_ctx(n);
     ws_set_kcos(kcos);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
-    if (fused_mode() >= 7) {
+    if (fused_transforms()) {
         launch_spec2grid_mma3(E.stream, c, W.d_inv, 1);
-    } else if (fused_mode() >= 5) {
-        launch_spec2grid_mma2(E.stream, c, W.d_inv, 1);
-    } else if (fused_mode() >= 3) {
-        launch_spec2grid_mma(E.stream, c, W.d_inv, 1);
-    } else if (use_fused_inv()) {
-        launch_spec2grid_fused(E.stream, c, W.d_inv, 1);
     } else {
         launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
         launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
@@ -137,10 +131,8 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
 int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
-    if (fused_mode() >= 6) {  // the model step's default forward kernel (the workspace is a scratch arena)
+    if (fused_transforms()) {  // the model step's default forward kernel (the workspace is a scratch arena)
         launch_grid2spec_mma2(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1, 0);
-    } else if (use_fused()) {
-        launch_grid2spec_fused(E.stream, c, FM_PLAIN, W.d_fwd, W.d_out, 1);
     } else {
         launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
         launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);

@@ -455,20 +455,17 @@ __global__ void __launch_bounds__(256) k_ens_reduce(const double *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
-// SPDY_FUSED selects the transform kernels: 7 (default) = spec -> grid through k_spec2grid_mma3 (fused_mma3.cu),
-// grid -> spec through ONE mixed-mode launch of k_grid2spec_mma2 (fused_mma2.cu); 6 / 5 = second-generation DMMA + TMA
-// kernels both ways / spec -> grid only; 4 / 3 = first DMMA kernels (fused_mma.cu) both ways / spec -> grid only;
-// 0 = separate FFT and Legendre kernels both ways; 1 = the first-generation fused kernels of fused.cu both ways,
-// 2 = fused.cu for spec -> grid only.  See DESIGN.md sections 4 and 8 for the measurements behind the default.
-static int fused_mode() {
+// SPDY_FUSED selects the transform kernels: default = the fused kernels (spec -> grid: k_spec2grid_mma3, fused_mma3.cu;
+// grid -> spec: ONE mixed-mode launch of k_grid2spec_mma2, fused_mma2.cu); SPDY_FUSED=0 = separate Legendre and FFT
+// kernels both ways (transforms.cu), kept as the unfused cross-check of the parity tests.
+static bool fused_transforms() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("SPDY_FUSED");
-        v = s ? atoi(s) : 7;
+        v = (s && atoi(s) == 0) ? 0 : 1;
     }
-    return v;
+    return v != 0;
 }
-static bool use_fused() { return fused_mode() == 1; }
 // SPDY_FUSE_PHYS=1 runs the grid-point dynamics and the column physics of a column in one kernel.  Measured: 34 loads
 // and 34 stores per column less DRAM traffic but the same time (0.884 ms vs 0.234 + 0.650 ms at 512 members): the
 // physics is bound by latency/issue at 12 warps per SM, not by bandwidth, so the default keeps the two kernels.
@@ -480,28 +477,9 @@ static bool fuse_dyn_physics() {
     }
     return v != 0;
 }
-static bool use_fused_inv() { return fused_mode() == 1 || fused_mode() == 2; }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
-    if (fused_mode() >= 7) {  // third generation: parity-pure DMMA over latitude octets (fused_mma3.cu)
+    if (fused_transforms()) {  // parity-pure DMMA over latitude octets + two-stage FFT, Fourier rows stay in shared memory
         launch_spec2grid_mma3(E.stream, c, d, n);
-        prof_mark(E.stream, PC_FFT_INV);
-        COUNT(1);
-        return;
-    }
-    if (fused_mode() >= 5) {  // second generation: 8 Legendre (DMMA) warps + 8 two-stage FFT warps
-        launch_spec2grid_mma2(E.stream, c, d, n);
-        prof_mark(E.stream, PC_FFT_INV);
-        COUNT(1);
-        return;
-    }
-    if (fused_mode() >= 3) {  // Legendre on the FP64 tensor cores + whole-line FFT, Fourier array in shared memory
-        launch_spec2grid_mma(E.stream, c, d, n);
-        prof_mark(E.stream, PC_FFT_INV);
-        COUNT(1);
-        return;
-    }
-    if (use_fused_inv()) {  // Legendre + FFT in one kernel, Fourier array stays in shared memory (fused.cu)
-        launch_spec2grid_fused(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
         return;
@@ -515,27 +493,9 @@ static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
 // sparse: the outputs feed the model's spectral step, which reads the rows inside the nsh2 mask only
 static void run_forward_lists(const Ctx &c, FwdDesc *const *lists, const int *counts, const FwdOut *outs, int nout,
                               int sparse = 0) {
-    if (fused_mode() >= 7 && lists == E.d_fwd) {  // the step's 73 fields in ONE launch of the fused forward kernel
+    if (fused_transforms() && lists == E.d_fwd) {  // the step's 73 fields in ONE launch of the fused forward kernel
         launch_grid2spec_mma2(E.stream, c, FM_ALL, E.d_fwd_all, outs, E.n_fwd_all, sparse);
         COUNT(1);
-        prof_mark(E.stream, PC_FFT_FWD);
-        return;
-    }
-    if (fused_mode() >= 6) {  // second-generation fused forward kernel (fused_mma2.cu); operands are scratch fields
-        for (int m = 0; m < FM_NMODES; m++)
-            if (counts[m]) launch_grid2spec_mma2(E.stream, c, m, lists[m], outs, counts[m], 0), COUNT(1);
-        prof_mark(E.stream, PC_FFT_FWD);
-        return;
-    }
-    if (fused_mode() == 4) {  // FFT + Legendre on the FP64 tensor cores in one kernel per loader mode (fused_mma.cu)
-        for (int m = 0; m < FM_NMODES; m++)
-            if (counts[m]) launch_grid2spec_mma(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
-        prof_mark(E.stream, PC_FFT_FWD);
-        return;
-    }
-    if (use_fused()) {
-        for (int m = 0; m < FM_NMODES; m++)
-            if (counts[m]) launch_grid2spec_fused(E.stream, c, m, lists[m], outs, counts[m]), COUNT(1);
         prof_mark(E.stream, PC_FFT_FWD);
         return;
     }
@@ -554,12 +514,8 @@ static void run_forward_plain(const Ctx &c, const std::vector<FieldRef> &src, co
     CK(cudaMemcpyAsync(E.d_fwd_tmp, f.data(), f.size() * sizeof(FwdDesc), cudaMemcpyHostToDevice, E.stream));
     CK(cudaMemcpyAsync(E.d_out_tmp, o.data(), o.size() * sizeof(FwdOut), cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    if (use_fused()) {
-        launch_grid2spec_fused(E.stream, c, mode, E.d_fwd_tmp, E.d_out_tmp, (int)f.size());
-    } else {
-        launch_fft_fwd(E.stream, c, mode, E.d_fwd_tmp, (int)f.size(), E.L.four);
-        launch_legendre_dir(E.stream, c, E.d_out_tmp, (int)f.size(), E.L.four);
-    }
+    launch_fft_fwd(E.stream, c, mode, E.d_fwd_tmp, (int)f.size(), E.L.four);
+    launch_legendre_dir(E.stream, c, E.d_out_tmp, (int)f.size(), E.L.four);
     COUNT(2);
     CK(cudaStreamSynchronize(E.stream));
 }
@@ -586,12 +542,8 @@ static void run_forcing(const Ctx &c, int imode) {
         CK(cudaMemcpy(d_f, f, sizeof(f), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_o, o, sizeof(o), cudaMemcpyHostToDevice));
     }
-    if (use_fused()) {
-        launch_grid2spec_fused(E.stream, c, FM_PLAIN, d_f, d_o, 2);
-    } else {
-        launch_fft_fwd(E.stream, c, FM_PLAIN, d_f, 2, L.four);
-        launch_legendre_dir(E.stream, c, d_o, 2, L.four);
-    }
+    launch_fft_fwd(E.stream, c, FM_PLAIN, d_f, 2, L.four);
+    launch_legendre_dir(E.stream, c, d_o, 2, L.four);
     launch_masked_copy(E.stream, c, REF_SCR | L.sfwd, E.off_tcorh, NSP, imode, 1.0);
     launch_masked_copy(E.stream, c, REF_SCR | (L.sfwd + NSP), E.off_qcorh, NSP, imode, 1.0);
     COUNT(4);
@@ -604,7 +556,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     // spectral pre-operators: geopotential (time level 1), uvspec, grad(ps)
     launch_geopotential(E.stream, c, E.off[V_t], E.off[V_phis], E.off[V_phi]);
     // k_spec2grid_mma3 reads the rows inside the nsh2 mask only: the pre-operators skip the other 47 % of each field
-    const int tri = fused_mode() >= 7 ? 1 : 0;
+    const int tri = fused_transforms() ? 1 : 0;
     launch_uvspec(E.stream, c, E.off[V_vor] + tl2, E.off[V_div] + tl2, REF_SCR | L.ucos, REF_SCR | L.vcos, KX, tri);
     launch_uvspec(E.stream, c, E.off[V_vor] + 7ll * NSP, E.off[V_div] + 7ll * NSP, REF_SCR | L.ucosp8, REF_SCR | L.vcosp8, 1, tri);
     launch_gradient(E.stream, c, E.off[V_ps] + (long long)(j2 - 1) * NSP, REF_SCR | L.dpx, REF_SCR | L.dpy, tri);

@@ -15,11 +15,7 @@
 // Measured (512 members, 77 fields): 0.469 ms against 0.496 for k_spec2grid_mma2.  A variant with all eight FFT warps
 // on one pass (one item per warp and stage, one exchange double buffer, 175 KB) was slower (0.621 ms: twice the
 // barriers per latitude, and its eight-way item switch cost 1.8 KB of spills in the Legendre warps).
-#include <cuda.h>
-#include <stdio.h>
-#include <stdlib.h>
-
-#include "kernels.h"
+#include "fused_common.cuh"
 
 namespace spdy {
 
@@ -144,7 +140,7 @@ __device__ __forceinline__ void s2g3_L(const Ctx &c, const InvDesc *__restrict__
     }
 }
 
-struct StExch1 {  // StExchK (fused_mma2.cu) without the scaling
+struct StExch1 {  // StExchK (fused_common.cuh) without the scaling
     double *p;
     __device__ __forceinline__ void operator()(int i, double v) const { p[(i >> 3) * 32] = v; }
 };

@@ -60,23 +60,15 @@ struct ImplTables {  // depends on the time step (implicit.f90:83-218): three in
     double xj[KX * KX * 64];          // (k,k1,l)
     double dhsx[KX];
 };
-constexpr int PQ_KTOT = 143;  // sum over m of ceil((32 - m) / 4)
-constexpr int PD_TTOT = 79;   // sum over m of ceil((min(30, 31 - m) + 1) / 8)
 constexpr int PQ2_KTOT = 155; // sum over m of the 4-term k-slices of even n plus those of odd n (fused_mma3.cu)
 constexpr int PD2_TTOT = 93;  // sum over m of the 8-row tiles of even n plus those of odd n (fused_mma2.cu)
 struct GlobTables {
     double cpol[MX * NX * IY];  // [m][n][j]  (unique half of the reference's duplicated re/im cpol)
-    double cpolj[MX * IY * NX]; // [m][j][n]  same values, latitude-major slices for the fused transforms
-    // DMMA A fragments of the fused spec->grid kernel (fused_mma.cu): [latitude quad 6][k-slice 143][16] =
-    // P(m, n, j) with n = 4s + i%4, j = 4jq + i/4 (hemisphere-0 half of the fragment); 0 outside the nsh2 mask
-    double pq_inv[6 * PQ_KTOT * 16];
-    // DMMA A fragments of the fused grid->spec kernel: [quad 6][n-tile 79][k-slice 2][lane 32] =
-    // sgn(hemi, n) * wt(j) * P(m, n, j) with n = 8nt + lane/4, j = 4jq + lane%4, hemi = k-slice; 0 outside the mask
-    // parity-pure DMMA A fragments of the third-generation spec->grid kernel: [latitude octet 3][k-slice 155][lane 32] =
-    // P(m, n, j) with n = parity + 2 * (4s + lane%4), j = 8jo + lane/4; per m the even-n slices, then the odd-n slices
+    // parity-pure DMMA A fragments of the fused spec->grid kernel: [latitude octet 3][k-slice 155][lane 32] =
+    // P(m, n, j) with n = parity + 2 * (4s + lane%4), j = 8jo + lane/4; per m the even-n slices, then the odd-n slices;
+    // 0 outside the nsh2 mask
     double pq_inv2[3 * PQ2_KTOT * 32];
-    double pq_dir[6 * PD_TTOT * 2 * 32];
-    // parity-pure DMMA A fragments of the second-generation grid->spec kernel: [quad 6][tile 93][lane 32] =
+    // parity-pure DMMA A fragments of the fused grid->spec kernel (Gaussian weights folded in): [quad 6][tile 93][lane 32] =
     // wt(j) * P(m, n, j) with n = parity + 2 * (8 * i + lane/4), j = 4jq + lane%4; per m the even-n tiles, then the odd-n tiles
     double pq_dir2[6 * PD2_TTOT * 32];
     double el2[NSPC], elm2[NSPC], trfilt[NSPC], gradym[NSPC], gradyp[NSPC], uvdx[NSPC], uvdym[NSPC], uvdyp[NSPC],

@@ -300,42 +300,9 @@ void build_tables(ConstTables &C, GlobTables &G) {
                     double v = P(m, n);
                     if (fabs(v) <= FL(1.e-30)) v = 0.0;
                     G.cpol[(m * NX + n) * IY + j] = v;
-                    G.cpolj[(m * IY + j) * NX + n] = v;
                 }
         }
-        // ---- pre-swizzled DMMA fragments of the fused spec->grid kernel (fused_mma.cu)
-        {
-            int koff = 0;
-            for (int m = 0; m < MX; m++) {
-                const int ks = (32 - m + 3) / 4, nmax = 31 - m;
-                for (int jq = 0; jq < IY / 4; jq++)
-                    for (int s = 0; s < ks; s++)
-                        for (int L = 0; L < 16; L++) {
-                            const int n = 4 * s + (L & 3), j = 4 * jq + (L >> 2);
-                            G.pq_inv[((size_t)jq * PQ_KTOT + koff + s) * 16 + L] =
-                                (n <= nmax) ? G.cpol[(m * NX + n) * IY + j] : 0.0;
-                        }
-                koff += ks;
-            }
-        }
-        // ---- pre-swizzled DMMA fragments of the fused grid->spec kernel (Gaussian weights folded in)
-        {
-            int toff = 0;
-            for (int m = 0; m < MX; m++) {
-                const int nmax = (30 < 31 - m) ? 30 : 31 - m, nt = (nmax + 1 + 7) / 8;
-                for (int jq = 0; jq < IY / 4; jq++)
-                    for (int i = 0; i < nt; i++)
-                        for (int ks = 0; ks < 2; ks++)
-                            for (int L = 0; L < 32; L++) {
-                                const int n = 8 * i + (L >> 2), j = 4 * jq + (L & 3);
-                                double v = (n <= nmax) ? C.wt[j] * G.cpol[(m * NX + n) * IY + j] : 0.0;
-                                if (ks && (n & 1)) v = -v;
-                                G.pq_dir[(((size_t)jq * PD_TTOT + toff + i) * 2 + ks) * 32 + L] = v;
-                            }
-                toff += nt;
-            }
-        }
-        // ---- parity-pure fragments of the third-generation fused spec->grid kernel (fused_mma3.cu): M = 8 latitudes
+        // ---- parity-pure DMMA fragments of the fused spec->grid kernel (fused_mma3.cu): M = 8 latitudes
         {
             int koff = 0;
             for (int m = 0; m < MX; m++) {
@@ -353,7 +320,7 @@ void build_tables(ConstTables &C, GlobTables &G) {
             }
             if (koff != PQ2_KTOT) abort();
         }
-        // ---- parity-pure fragments of the second-generation fused grid->spec kernel (fused_mma2.cu): the N/S fold
+        // ---- parity-pure DMMA fragments of the fused grid->spec kernel (fused_mma2.cu): the N/S fold
         //      (legendre.f90:196-203) is done on the Fourier rows, so a tile needs one k-slice instead of two
         {
             int toff = 0;

@@ -20,7 +20,6 @@ namespace spdy {
 #define FFT_MINBLOCKS 3
 #endif
 #include "fft96_gen.cuh"
-#include "fft96_reg_gen.cuh"
 
 // ------------------------------------------------------------------------------------------- Legendre inverse
 // One warp = one (field, m-pair); pairs (m, 30-m) balance the triangular truncation: 34 n-terms per pair.

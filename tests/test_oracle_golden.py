@@ -1,6 +1,9 @@
 """Pin the oracle against what the reference ships: the fixture coordinates are an exact known-answer
-test of geometry.f90:89-110 + initialization.f90:85-87; the fixture fields are a coarse end-to-end check because the
-default SST-anomaly file (pyspeedy/data/sst_anomaly.nc) is missing from the mount."""
+test of geometry.f90:89-110 + initialization.f90:85-87; the fixture fields (day 1 and day 3 of the reference's own
+test, pyspeedy/tests/test_speedy.py:27-50) are a coarse end-to-end check because the default SST-anomaly file
+(pyspeedy/data/sst_anomaly.nc) is missing from the mount.  `test_sst_anomaly_explains_the_fixture_residual` shows that
+the residual of that check has the size, the vertical/latitudinal structure and the land/Antarctica attenuation of the
+model's response to a +-1 K SST anomaly -- on both fixture days, for all six variables."""
 import os
 
 import numpy as np
@@ -55,6 +58,79 @@ def test_fixture_fields_coarse(one_day):
             d = (a - ref)[:, land]
             assert np.sqrt(np.mean(d ** 2)) < 0.06
             assert np.sqrt(np.mean((a - ref)[:, :6, :] ** 2)) < 0.02  # Antarctica: 6 southernmost rows, all levels
+
+
+NAMES = {"u": "u_grid", "v": "v_grid", "t": "t_grid", "q": "q_grid", "phi": "phi_grid", "ps": "ps_grid"}
+
+
+def _export(st):
+    """float32, levels increasing with height, (lev, lat, lon): the layout of the reference's exporter."""
+    c = st.clone()
+    c.spectral2grid()
+    out = {}
+    for k, v in NAMES.items():
+        a = c[v].astype(np.float32)
+        out[k] = a[:, :, ::-1].transpose(2, 1, 0) if a.ndim == 3 else a.T
+    return out
+
+
+def _run_days(oracle, sst_anom, snaps=(1, 3)):
+    st = oracle.State(n_months=1)
+    ctl = oracle.Control((1982, 1, 1, 0, 0), (1982, 1, 4, 0, 0))
+    oracle.load_default_bc(st)
+    if sst_anom is not None:
+        st["sst_anom"] = np.repeat(sst_anom[:, :, None], 3, axis=2)
+    assert st.init(ctl) == 0
+    out = {}
+    for day in range(1, max(snaps) + 1):
+        for _ in range(36):
+            assert st.step(ctl) == 0
+        if day in snaps:
+            out[day] = _export(st)
+    return out
+
+
+@pytest.fixture(scope="module")
+def sst_runs(oracle):
+    base = _run_days(oracle, None)
+    anom = np.random.default_rng(7).choice([-1.0, 1.0], size=(96, 48))  # i.i.d. +-1 K at every sea point
+    return base, _run_days(oracle, anom)
+
+
+@pytest.mark.parametrize("day, fixture", [(1, "fixture_1982-01-02.npz"), (3, "fixture_1982-01-04.npz")])
+def test_fixture_fields_coarse_both_days(sst_runs, day, fixture):
+    """Both golden files of the reference's test (36 and 108 steps from the rest state), zero SST anomaly."""
+    base, _ = sst_runs
+    fx = np.load(os.path.join(GOLDEN, fixture))
+    for k in NAMES:
+        ref = fx[k][0]
+        rms = np.sqrt(np.mean((base[day][k] - ref) ** 2)) / (ref.max() - ref.min())
+        assert rms < 1.5e-2, (day, k, rms)
+
+
+@pytest.mark.parametrize("day, fixture", [(1, "fixture_1982-01-02.npz"), (3, "fixture_1982-01-04.npz")])
+def test_sst_anomaly_explains_the_fixture_residual(sst_runs, day, fixture):
+    """The residual (zero-anomaly oracle minus reference fixture) against the oracle's response to a random +-1 K SST
+    anomaly (sea_model.f90:218-221,276-296: the anomaly enters sst_am only).  Measured ratios residual/response:
+    0.74-1.10 (day 1), 0.87-1.04 (day 3); correlation of the (level, latitude) RMS profiles 0.89-0.98."""
+    base, pert = sst_runs
+    fx = np.load(os.path.join(GOLDEN, fixture))
+    bc = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "pyspeedy_b200", "data", "example_bc.npz"))
+    land = bc["lsm"].T > 0.5
+    for k in NAMES:
+        resp = pert[day][k] - base[day][k]
+        res = base[day][k] - fx[k][0]
+        ratio = np.sqrt(np.mean(res ** 2)) / np.sqrt(np.mean(resp ** 2))
+        assert 0.6 < ratio < 1.6, (day, k, ratio)  # same magnitude for every variable
+        ax = 2 if resp.ndim == 3 else 1  # zonal RMS -> (level, latitude) profile: largest where the response is largest
+        prof_resp, prof_res = np.sqrt((resp ** 2).mean(axis=ax)).ravel(), np.sqrt((res ** 2).mean(axis=ax)).ravel()
+        assert np.corrcoef(prof_resp, prof_res)[0, 1] > 0.85, (day, k)
+    resp, res = pert[day]["t"] - base[day]["t"], base[day]["t"] - fx["t"][0]
+    rms = lambda x: float(np.sqrt(np.mean(x ** 2)))  # noqa: E731
+    # away from the sea the residual is attenuated exactly as the SST response is: land, Antarctica (6 southern rows)
+    assert 0.6 < rms(res[:, land]) / rms(resp[:, land]) < 1.6
+    assert 0.6 < rms(res[:, :6]) / rms(resp[:, :6]) < 1.6
+    assert rms(res[:, land]) < 0.5 * rms(res[0][~land]) and rms(resp[:, land]) < 0.5 * rms(resp[0][~land])
 
 
 def test_missing_values_only_where_masked():

@@ -24,6 +24,20 @@ def synth_spec(n, seed=2024, scale=1.0):
 
 
 def relerr(a, b):
-    """max |a-b| / max |b| -- the norm the parity tolerances are stated in."""
+    """max |a-b| / max |b| over ONE variable -- the norm the parity tolerances are stated in."""
     den = np.abs(b).max()
     return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def relerr_fields(a, b):
+    """Batched transforms: axis 0 runs over independent fields; every field is measured against ITS OWN max|b_f| and the
+    worst field is returned, so a low-amplitude field cannot hide behind a large one."""
+    a, b = np.asarray(a), np.asarray(b)
+    ax = tuple(range(1, b.ndim))
+    den = np.abs(b).max(axis=ax)
+    return float((np.abs(a - b).max(axis=ax) / np.where(den > 0, den, 1.0)).max())
+
+
+def field_scales(n, seed):
+    """Per-field amplitudes spread over six decades (makes the per-field norm bite)."""
+    return 10.0 ** np.random.default_rng(seed).uniform(-3, 3, size=n)

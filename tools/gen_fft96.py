@@ -516,26 +516,12 @@ def main():
         report.append("  B%d: %d outputs, %d flops" % (q, len(slots), fl))
     out.append("#define FFTF_NA %d\n#define FFTF_NB %d\n" % (nA, nB))
 
-    if LEVEL_ORDER:  # nested call for the register variant: return the text only
-        return out
     path = os.path.join(ROOT, "pyspeedy_b200/csrc/fft96_gen.cuh")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as fp:
         fp.write("\n".join(out))
-    # Register-exchange variant: the same items with the exchange array private to the thread (stride 1), for
-    # kernels in which one thread transforms a whole line (fused Legendre+FFT kernels).  Names get an `r` prefix.
-    LEVEL_ORDER = True
-    out_reg = main()
-    LEVEL_ORDER = False
-    reg = "\n".join(out_reg).replace("fftb_", "rfftb_").replace("fftf_", "rfftf_").replace(" * FFT_LS]", "]")
-    reg = reg.replace("#define FFTB_NA", "#define RFFTB_NA").replace("#define FFTB_NB", "#define RFFTB_NB")
-    reg = reg.replace("#define FFTF_NA", "#define RFFTF_NA").replace("#define FFTF_NB", "#define RFFTF_NB")
-    reg = reg.replace("FFT_LS = lane stride (doubles).", "Exchange array private to the thread (stride 1).")
-    rpath = os.path.join(ROOT, "pyspeedy_b200/csrc/fft96_reg_gen.cuh")
-    with open(rpath, "w") as fp:
-        fp.write(reg)
     print("\n".join(report))
-    print("wrote", path, "and", rpath)
+    print("wrote", path)
 
 
 if __name__ == "__main__":
