@@ -53,6 +53,7 @@ int spdy_shape(int64_t state, int var, int *dims /* [5] */, int *ndim);
 int spdy_run_steps(const int64_t *states, const int64_t *controls, int n_members, int nsteps, int *error_codes);
 int spdy_reserve(int n_members);            /* pre-size the device arenas */
 int spdy_set_device(int ordinal);           /* select the GPU (before the first state is created) */
+int spdy_device_count(void);                /* CUDA devices visible to this process (0 without a driver) */
 int spdy_synchronize(void);
 /* elapsed device time (ms) of the last spdy_run_steps / spdy_parallel_step call, CUDA events on the launch stream */
 float spdy_last_elapsed_ms(void);
@@ -63,12 +64,39 @@ int spdy_profiler_stop(void);
 /* The member's model date as the device calendar holds it (control_params%model_datetime of the bound control,
    model_control.f90:113-163); out = {year, month, day, hour, minute}.  Returns 0, or -1 for an unknown handle. */
 int spdy_get_model_datetime(int64_t state, int *out);
-/* partial sums for ensemble mean / spread of a grid variable over the listed members:
- * sum[i] = sum_m x_m[i], sumsq[i] = sum_m (x_m[i]-shift[i])^2, both device-resident results copied to host */
+/* partial sums for ensemble mean / spread of ONE registry array variable over the listed members:
+ * sum[i] = sum_m x_m[i], sumsq[i] = sum_m (x_m[i]-shift[i])^2, reduced on the device, summed over all ranks when a
+ * communicator is up (spdy_comm_init), copied to the host */
 int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const double *shift, double *sum, double *sumsq);
-/* same, leaving results on the device for an NCCL all-reduce: returns device pointers (2 * nelem doubles) */
+/* same for this rank only, leaving the results on the device: returns a device pointer (2 * nelem doubles) */
 int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **sum_sumsq_dev,
                               size_t *nelem);
+/* transform_spectral2grid (.j2:94-103) for the listed members and, in the epilogue of the same pass, ensemble mean and
+ * spread (std, ddof 0: examples/Ensemble_forecast.ipynb cells 12, 16) of the six default outputs u, v, t, q, phi, ps on
+ * the grid over all n_total members of all ranks: one in-stream ncclAllReduce(sum, double), one device-to-host copy, one
+ * synchronisation.  out = 2 x 188,928 doubles (mean, then spread; variables one after another in Fortran order), or NULL
+ * to leave them on the device (spdy_ensemble_stats_device_ptr). */
+int spdy_ensemble_mean_spread(const int64_t *states, int n_members, long long n_total, double *out);
+void *spdy_ensemble_stats_device_ptr(void);
+/* get_<v> (.j2:264-290) for every listed member in one call: dst[member][Fortran-order array], float64 or (as_f32) cast
+ * to float32 on the device as pyspeedy/speedy.py:443 does on the host */
+int spdy_ensemble_get(const int64_t *states, int n_members, int var, void *dst, size_t bytes, int as_f32);
+/* check (.j2:81-91) for every listed member in one call */
+int spdy_batch_check(const int64_t *states, int n_members, int *error_codes);
+/* datetime containers updated in place; the batched form stores one date in every listed container */
+int spdy_set_datetime(int64_t dt, int year, int month, int day, int hour, int minute);
+int spdy_set_datetimes(const int64_t *dts, int n, const int *ymdhm /* [5] */);
+
+/* ---- multi-GPU: one process per GPU, members sharded across ranks, no communication inside a time step (.j2:58-79:
+ * members are independent); NCCL (loaded with dlopen) only for the ensemble diagnostics above.  The 128-byte id made by
+ * rank 0 reaches the other ranks through the launcher (pyspeedy_b200/distributed.py: file rendezvous under torchrun). */
+int spdy_comm_unique_id(void *id128);
+int spdy_comm_init(int rank, int world, const void *id128); /* after spdy_set_device */
+int spdy_comm_rank(void);
+int spdy_comm_world(void);
+int spdy_comm_allreduce(double *host_inout, int n /* <= 64 */, int op /* 0 sum, 1 max */);
+int spdy_comm_barrier(void);
+int spdy_comm_destroy(void);
 
 /* copy the complete device state of `src` into every member of `dst` (ensemble set-up from one initialised member) */
 int spdy_clone_state(int64_t src, const int64_t *dst, int n);

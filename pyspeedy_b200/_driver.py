@@ -34,6 +34,8 @@ def lib():
                 f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; "
                 "g.build()').  pyspeedy_b200 has no CPU path."
             )
+        # ctypes.CDLL releases the GIL during calls; every entry point of the library takes one process-wide lock
+        # (engine.cu: API_LOCK), so Python threads driving different Speedy instances are safe (and serialised)
         L = C.CDLL(LIB_PATH)
         i64, vp, ci = C.c_int64, C.c_void_p, C.c_int
         L.spdy_modelstate_init.restype = i64
@@ -65,6 +67,15 @@ def lib():
         L.spdy_kernel_launches.restype = C.c_longlong
         L.spdy_ensemble_sums.argtypes = [vp, ci, ci, vp, vp, vp]
         L.spdy_ensemble_sums_device.argtypes = [vp, ci, ci, vp, vp, vp]
+        L.spdy_ensemble_mean_spread.argtypes = [vp, ci, C.c_longlong, vp]
+        L.spdy_ensemble_stats_device_ptr.restype = vp
+        L.spdy_ensemble_get.argtypes = [vp, ci, ci, vp, C.c_size_t, ci]
+        L.spdy_batch_check.argtypes = [vp, ci, vp]
+        L.spdy_set_datetime.argtypes = [i64] + [ci] * 5
+        L.spdy_set_datetimes.argtypes = [vp, ci, vp]
+        L.spdy_comm_unique_id.argtypes = [vp]
+        L.spdy_comm_init.argtypes = [ci, ci, vp]
+        L.spdy_comm_allreduce.argtypes = [vp, ci, ci]
         L.spdy_table.argtypes = [C.c_char_p, vp, ci]
         L.spdy_batch_spec2grid.argtypes = [vp, vp, ci, ci]
         L.spdy_batch_grid2spec.argtypes = [vp, vp, ci]
@@ -123,6 +134,20 @@ class _SpeedyDriver:
         if lib().spdy_get_model_datetime(int(state_cnt), _ptr(out)) != 0:
             raise ValueError("unknown state container")
         return tuple(int(x) for x in out)
+
+    @staticmethod
+    def set_datetime(container, year, month, day, hour, minute):
+        """Extension: update a datetime container in place (the reference frees and re-creates it)."""
+        if lib().spdy_set_datetime(int(container), int(year), int(month), int(day), int(hour), int(minute)) != 0:
+            raise ValueError("unknown datetime container")
+
+    @staticmethod
+    def set_datetimes(containers, date_value):
+        """Extension: store one date in every listed container with a single driver call."""
+        c = np.ascontiguousarray(containers, dtype=np.int64)
+        d = np.array([date_value.year, date_value.month, date_value.day, date_value.hour, date_value.minute], dtype=np.int32)
+        if lib().spdy_set_datetimes(_ptr(c), c.shape[0], _ptr(d)) != 0:
+            raise ValueError("unknown datetime container")
 
     @staticmethod
     def close_datetime(container):
@@ -193,6 +218,57 @@ class _SpeedyDriver:
             raise RuntimeError(f"spdy_ensemble_sums({var_name}) failed: {rc}")
         shp = tuple(e["shape"])
         return out1.reshape(shp, order="F"), out2.reshape(shp, order="F")
+
+    # the six default outputs in the order of spdy_ensemble_mean_spread
+    STATS_VARS = ("u_grid", "v_grid", "t_grid", "q_grid", "phi_grid", "ps_grid")
+
+    @staticmethod
+    def ensemble_mean_spread(states, n_total=None):
+        """spectral2grid of the listed members + ensemble mean and spread (std, ddof=0) of the six default outputs over
+        all ``n_total`` members of all ranks (default: the listed members): partial sums in the transform's epilogue, one
+        NCCL all-reduce when a communicator is up, one device-to-host copy.  Returns {var: (mean, spread)}."""
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        ntot = 5 * 96 * 48 * 8 + 96 * 48
+        out = np.empty(2 * ntot)
+        rc = lib().spdy_ensemble_mean_spread(_ptr(s), s.shape[0], int(n_total or s.shape[0]), _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"spdy_ensemble_mean_spread failed: {rc}")
+        res, o = {}, 0
+        for v in _SpeedyDriver.STATS_VARS:
+            shp = tuple(REGISTRY[VAR_ID[v]]["shape"])
+            n = int(np.prod(shp))
+            res[v] = (out[o:o + n].reshape(shp, order="F"), out[ntot + o:ntot + o + n].reshape(shp, order="F"))
+            o += n
+        return res
+
+    @staticmethod
+    def ensemble_get(states, var_name, dtype=np.float64):
+        """``get_<var>`` of every listed member in one driver call: array of shape (n_members,) + reversed(var shape),
+        C-ordered, i.e. ``out[i].T`` is what ``get_<var>(states[i])`` returns.  ``dtype=np.float32`` casts on the device."""
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        e = REGISTRY[VAR_ID[var_name]]
+        if e["shape"] is None or e["dtype"] not in ("f8", "c16") or var_name == "sst_anom":
+            raise ValueError(f"ensemble_get supports the float64 / complex128 array variables, not {var_name}")
+        f32 = np.dtype(dtype) == np.float32
+        shp = tuple(reversed(e["shape"]))
+        if e["dtype"] == "c16":
+            if f32:
+                raise ValueError("complex variables are returned as complex128")
+            out = np.empty((s.shape[0],) + shp, dtype=np.complex128)
+        else:
+            out = np.empty((s.shape[0],) + shp, dtype=np.float32 if f32 else np.float64)
+        rc = lib().spdy_ensemble_get(_ptr(s), s.shape[0], e["id"], _ptr(out), out.nbytes, 1 if f32 else 0)
+        if rc != 0:
+            raise RuntimeError(f"spdy_ensemble_get({var_name}) failed: {rc}")
+        return out
+
+    @staticmethod
+    def batch_check(states):
+        """``check`` of every listed member in one driver call; int32 error codes."""
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        err = np.zeros(s.shape[0], dtype=np.int32)
+        lib().spdy_batch_check(_ptr(s), s.shape[0], _ptr(err))
+        return err
 
     @staticmethod
     def profile_step(state_containers, control_containers):

@@ -41,10 +41,9 @@ class DiagnosticCheck(BaseCallback):
     def __call__(self, model_instance):
         if self.skip_flag(model_instance):
             return
-        if isinstance(model_instance, Speedy):
-            model_instance = [model_instance]
-        for _member in model_instance:
-            _member.check()
+        # a failing check raises a RuntimeError; for an ensemble the members are checked by ONE batched driver call
+        # (the reference loops over the members: pyspeedy/callbacks.py:103-111)
+        model_instance.check()
 
 
 class ModelCheckpoint(BaseCallback):
@@ -67,6 +66,28 @@ class ModelCheckpoint(BaseCallback):
             self.dataframe = model_df
         else:
             self.dataframe = Dataset.merge((self.dataframe, model_df))
+
+
+class EnsembleStatistics(BaseCallback):
+    """Extension (no reference counterpart; the notebook examples/Ensemble_forecast.ipynb computes these with xarray from a
+    ModelCheckpoint of all members): keep the time series of the ensemble mean and spread (std, ddof=0) of the six
+    default outputs.  The sums are formed on the GPU in the epilogue of the batched spectral2grid and reduced over all
+    ranks of a sharded ensemble by one NCCL all-reduce per output time (``SpeedyEns.mean_and_spread``)."""
+
+    def __init__(self, interval=36, verbose=False, spinup_date=None, variables=None):
+        self.variables = DEFAULT_OUTPUT_VARS if variables is None else variables
+        super().__init__(verbose=verbose, interval=interval, spinup_date=spinup_date)
+        self.times, self.mean, self.spread = [], {v: [] for v in self.variables}, {v: [] for v in self.variables}
+
+    def __call__(self, model_instance):
+        if self.skip_flag(model_instance):
+            return
+        stats = model_instance.mean_and_spread(self.variables)
+        self.times.append(model_instance.current_date)
+        for v in self.variables:
+            self.mean[v].append(stats[v][0])
+            self.spread[v].append(stats[v][1])
+        self.print_msg(f"Ensemble statistics at {model_instance.current_date}.")
 
 
 class XarrayExporter(BaseCallback):

@@ -81,6 +81,7 @@ static void ws_move(const double *host_in, double *host_out, long long off, long
 extern "C" {
 
 int spdy_batch_legendre_inv(const double *spec, double *four, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_set_kcos(1);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
@@ -90,6 +91,7 @@ int spdy_batch_legendre_inv(const double *spec, double *four, int n) {
     return 0;
 }
 int spdy_batch_fourier_inv(const double *four, double *grid, int kcos, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_set_kcos(kcos);
     ws_move(four, nullptr, WS_FOUR, NFOUR, n);
@@ -99,6 +101,7 @@ int spdy_batch_fourier_inv(const double *four, double *grid, int kcos, int n) {
     return 0;
 }
 int spdy_batch_fourier_dir(const double *grid, double *four, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
     launch_fft_fwd(E.stream, c, FM_PLAIN, W.d_fwd, 1, WS_FOUR);
@@ -107,6 +110,7 @@ int spdy_batch_fourier_dir(const double *grid, double *four, int n) {
     return 0;
 }
 int spdy_batch_legendre_dir(const double *four, double *spec, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_move(four, nullptr, WS_FOUR, NFOUR, n);
     launch_legendre_dir(E.stream, c, W.d_out, 1, WS_FOUR);
@@ -115,6 +119,7 @@ int spdy_batch_legendre_dir(const double *four, double *spec, int n) {
     return 0;
 }
 int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_set_kcos(kcos);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
@@ -129,6 +134,7 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
     return 0;
 }
 int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_move(grid, nullptr, WS_GRID, NG, n);
     if (fused_transforms()) {  // the model step's default forward kernel (the workspace is a scratch arena)
@@ -143,6 +149,7 @@ int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
 }
 
 int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, float *ms_per_rep, float *per_kernel_ms) {
+    API_LOCK;
     Ctx c = ws_ctx(n);
     ws_set_kcos(1);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
@@ -176,6 +183,8 @@ int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, 
     if (spec_out) ws_move(nullptr, spec_out, WS_SPEC, NSP, n);
     return 0;
 }
+
+}  // extern "C"
 
 // ---- ensemble set-up / output extensions ----------------------------------------------------------------------
 namespace spdy {
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(256) k_add_spec(const Ctx c, FieldRef src, lon
 extern "C" {
 // copy the complete device state of `src` into every member of `dst` (ensemble set-up from one initialised member)
 int spdy_clone_state(int64_t src, const int64_t *dst, int n) {
+    API_LOCK;
     Member *ms = member_of(src);
     if (!ms) return -1;
     for (int i = 0; i < n; i++) {
@@ -233,6 +243,7 @@ int spdy_clone_state(int64_t src, const int64_t *dst, int n) {
 // t_grid += N(0, sigma) i.i.d. per grid point, then t = grid2spec(t_grid) on time level 1 -- the perturbed-IC ensemble of
 // examples/Ensemble_forecast.ipynb cell 8, done for all listed members on the device (linear: t += grid2spec(noise))
 int spdy_perturb_temperature(const int64_t *hs, int n, unsigned long long seed, double sigma) {
+    API_LOCK;
     engine_init();
     const ScratchLayout &L = E.L;
     const int nt = prepare_members(hs, n);
@@ -251,6 +262,7 @@ int spdy_perturb_temperature(const int64_t *hs, int n, unsigned long long seed, 
 }
 // transform_spectral2grid for a list of members in one go (chunked)
 int spdy_batch_spectral2grid(const int64_t *hs, int n) {
+    API_LOCK;
     engine_init();
     const int nt = prepare_members(hs, n);
     for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
@@ -263,6 +275,7 @@ int spdy_batch_spectral2grid(const int64_t *hs, int n) {
 // one model step of the listed members with device events between kernel classes; ms[10] per class (summed over chunks):
 // forcing, pre-ops, legendre_inv, fft_inv, grid_dyn, physics, fft_fwd, legendre_dir, spec_step, post
 int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, int *err) {
+    API_LOCK;
     engine_init();
     if (!P.made) {
         for (int i = 0; i < 64; i++) CK(cudaEventCreate(&P.ev[i]));
@@ -290,53 +303,6 @@ int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, in
 
 extern "C" {
 // bracket a region for `ncu --profile-from-start off`
-int spdy_profiler_start(void) { return (int)cudaProfilerStart(); }
-int spdy_profiler_stop(void) { return (int)cudaProfilerStop(); }
+int spdy_profiler_start(void) { API_LOCK; return (int)cudaProfilerStart(); }
+int spdy_profiler_stop(void) { API_LOCK; return (int)cudaProfilerStop(); }
 }
-
-static double *g_sums = nullptr, *g_part = nullptr;
-static size_t g_sums_n = 0, g_part_n = 0;
-int spdy_ensemble_sums_device(const int64_t *states, int n_members, int var, const double *shift_dev, void **out, size_t *nelem) {
-    engine_init();
-    if (var < 0 || var >= SPDY_NVARS || E.off[var] < 0) return -1;
-    const long long n = E.nelem[var];
-    if ((size_t)n > g_sums_n) {
-        if (g_sums) CK(cudaFree(g_sums));
-        CK(cudaMalloc(&g_sums, 2 * n * sizeof(double)));
-        g_sums_n = n;
-    }
-    const int nt = prepare_members(states, n_members);
-    const int groups = (nt + ENS_TG - 1) / ENS_TG;
-    if ((size_t)groups * 2 * n > g_part_n) {
-        if (g_part) CK(cudaFree(g_part));
-        g_part_n = (size_t)groups * 2 * n;
-        CK(cudaMalloc(&g_part, g_part_n * sizeof(double)));
-    }
-    Ctx c = make_ctx(E.d_tiles, E.d_masks, nt);
-    k_ens_sums<<<dim3((unsigned)((n + 7) / 8), groups), 256, 0, E.stream>>>(c, E.off[var], n, shift_dev, g_part);
-    k_ens_reduce<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(g_part, groups, n, g_sums, g_sums + n);
-    COUNT(2);
-    CK(cudaStreamSynchronize(E.stream));
-    *out = g_sums;
-    *nelem = (size_t)n;
-    return 0;
-}
-int spdy_ensemble_sums(const int64_t *states, int n_members, int var, const double *shift, double *sum, double *sumsq) {
-    engine_init();
-    if (var < 0 || var >= SPDY_NVARS || E.off[var] < 0) return -1;
-    const long long n = E.nelem[var];
-    double *d_shift = nullptr;
-    if (shift) {
-        CK(cudaMalloc(&d_shift, n * sizeof(double)));
-        CK(cudaMemcpy(d_shift, shift, n * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    void *dev;
-    size_t ne;
-    spdy_ensemble_sums_device(states, n_members, var, d_shift, &dev, &ne);
-    CK(cudaMemcpy(sum, dev, n * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(sumsq, (double *)dev + n, n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (d_shift) CK(cudaFree(d_shift));
-    return 0;
-}
-
-}  // extern "C"

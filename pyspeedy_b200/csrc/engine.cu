@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -31,6 +32,12 @@ static inline void ck(cudaError_t e, const char *file, int line, const char *wha
 
 static long long g_launches = 0;
 #define COUNT(n) (g_launches += (n))
+
+// The engine keeps process-global state (handle tables, staging buffers, cached descriptors, graph executables) and
+// ctypes releases the GIL during calls: every C-ABI entry point takes this lock, so Python threads driving different
+// Speedy instances serialise on the library instead of racing (entry points call each other: recursive).
+static std::recursive_mutex g_api_mutex;
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g_api_mutex)
 
 // optional per-kernel-class device timing (spdy_profile_step): events between the stages of one step
 enum ProfClass { PC_FORCING = 0, PC_PREOPS, PC_LEG_INV, PC_FFT_INV, PC_GRID_DYN, PC_PHYSICS, PC_FFT_FWD, PC_LEG_DIR,
@@ -105,7 +112,7 @@ struct Engine {
     std::vector<Member> members;
     std::vector<Control> controls;
     std::vector<Datetime> dates;
-    std::vector<int> free_members;
+    std::vector<int> free_members, free_controls, free_dates;
     // chunk descriptors
     int *d_tiles = nullptr;
     unsigned *d_masks = nullptr;
@@ -120,6 +127,7 @@ struct Engine {
     int n_fwd_all = 0;
     int n_fwd[FM_NMODES] = {};
     FwdOut *d_out = nullptr;
+    InvDesc *d_inv_s2g = nullptr;  // the 41 fields of transform_spectral2grid (prognostics.f90:125-154)
     InvDesc *d_inv_tmp = nullptr;
     FwdDesc *d_fwd_tmp = nullptr;
     FwdOut *d_out_tmp = nullptr;
@@ -198,6 +206,19 @@ static void build_descriptor_lists() {
     }
     CK(cudaMalloc(&E.d_out, outs.size() * sizeof(FwdOut)));
     CK(cudaMemcpy(E.d_out, outs.data(), outs.size() * sizeof(FwdOut), cudaMemcpyHostToDevice));
+    {
+        std::vector<InvDesc> v;
+        for (int k = 0; k < KX; k++) {
+            v.push_back(InvDesc{REF_SCR | (L.ucos + (long long)k * NSP), L.ug + (long long)k * NG, 2, 0});
+            v.push_back(InvDesc{REF_SCR | (L.vcos + (long long)k * NSP), L.vg + (long long)k * NG, 2, 0});
+            v.push_back(InvDesc{E.off[V_t] + (long long)k * NSP, L.tg + (long long)k * NG, 1, 0});
+            v.push_back(InvDesc{E.off[V_tr] + (long long)k * NSP, L.trg + (long long)k * NG, 1, 0});
+            v.push_back(InvDesc{E.off[V_phi] + (long long)k * NSP, L.pphig + (long long)k * NG, 1, 0});
+        }
+        v.push_back(InvDesc{E.off[V_ps], L.pslg, 1, 0});
+        CK(cudaMalloc(&E.d_inv_s2g, v.size() * sizeof(InvDesc)));
+        CK(cudaMemcpy(E.d_inv_s2g, v.data(), v.size() * sizeof(InvDesc), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&E.d_inv_tmp, 128 * sizeof(InvDesc)));
     CK(cudaMalloc(&E.d_fwd_tmp, 128 * sizeof(FwdDesc)));
     CK(cudaMalloc(&E.d_out_tmp, 128 * sizeof(FwdOut)));
@@ -248,8 +269,10 @@ static void engine_init() {
     E.ready = true;
 }
 
+static void drop_step_graphs();  // cached graph executables hold arena addresses
 static void ensure_state_tiles(int ntiles) {
     if (ntiles <= E.cap_tiles) return;
+    drop_step_graphs();
     int ncap = std::max(ntiles, E.cap_tiles ? E.cap_tiles * 2 : 1);
     const size_t per_tile = (size_t)E.st_elems * TILE * sizeof(double);
     double *nst = nullptr;
@@ -279,6 +302,7 @@ static void ensure_state_tiles(int ntiles) {
 
 static void ensure_sst_months(int slabs) {  // slabs = n_months + 2
     if (slabs <= E.sst_months) return;
+    drop_step_graphs();
     const long long nelems = (long long)slabs * NG;
     double *ns = nullptr;
     const int cap = std::max(E.cap_tiles, 1);
@@ -297,6 +321,7 @@ static void ensure_sst_months(int slabs) {  // slabs = n_months + 2
 static void ensure_scratch(int ntiles) {
     ntiles = std::min(ntiles, E.chunk_tiles);
     if (ntiles <= E.scr_tiles) return;
+    drop_step_graphs();
     if (E.scr) CK(cudaFree(E.scr));
     CK(cudaMalloc(&E.scr, (size_t)E.L.total * TILE * sizeof(double) * ntiles));
     CK(cudaMemsetAsync(E.scr, 0, (size_t)E.L.total * TILE * sizeof(double) * ntiles, E.stream));
@@ -305,6 +330,7 @@ static void ensure_scratch(int ntiles) {
 
 static void ensure_desc(int n) {
     if (n <= E.desc_cap) return;
+    drop_step_graphs();
     if (E.d_tiles) CK(cudaFree(E.d_tiles)), CK(cudaFree(E.d_masks));
     E.desc_cap = std::max(n, 64);
     CK(cudaMalloc(&E.d_tiles, E.desc_cap * sizeof(int)));
@@ -356,10 +382,18 @@ __global__ void k_scatter(double *arena, long long tile_elems, int tile, int lan
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) arena[((long long)tile * tile_elems + off + i) * TILE + lane] = src[i];
 }
-__global__ void k_collect_err(const Ctx c, int *out, const int sticky) {  // out[tile_in_chunk*32 + lane]
+// Error codes of a driver call are STICKY: `out` (zeroed when the call starts) keeps the first non-zero code of every
+// member, and a member that fails is taken out of the call's active-lane mask, so that the remaining steps of a
+// multi-step call leave it exactly as the failing step left it (device calendar not advanced, speedy.f90:62-69) instead
+// of stepping a blown-up state that may turn into NaNs -- which pass check_diagnostics, every NaN comparison being false.
+__global__ void k_collect_err(const Ctx c, int *out, unsigned *masks) {  // out[tile_in_chunk*32 + lane]
     const int lane = threadIdx.x, t = blockIdx.x;
-    out[t * TILE + lane] = (int)slot(c, t, lane, SL_ERR);
-    (void)sticky;
+    if (!lane_active(c, t, lane)) return;
+    const int code = (int)slot(c, t, lane, SL_ERR);
+    if (code != 0 && out[t * TILE + lane] == 0) {
+        out[t * TILE + lane] = code;
+        atomicAnd(&masks[t], ~(1u << lane));
+    }
 }
 __global__ void k_spec_trunc(const Ctx c, FieldRef f, int nfields) {  // zero l > trunc (spectral.f90:309-314)
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
@@ -651,6 +685,11 @@ typedef std::tuple<const void *, const void *, const void *, const void *, const
     StepGraphKey;
 static std::map<StepGraphKey, StepGraph> g_step_graphs;
 static bool g_eager_done[2] = {false, false};  // statics inside the launchers are initialised by an eager run
+static void drop_step_graphs() {
+    for (auto &kv : g_step_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    g_step_graphs.clear();
+}
 static int graph_max_tiles() {
     static int v = -1;
     if (v < 0) {
@@ -664,7 +703,7 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
     const bool use_graph = ntc <= graph_max_tiles() && !P.on && g_eager_done[any_daily ? 1 : 0];
     if (!use_graph) {
         run_model_step(c, any_daily);
-        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, 0);
+        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, E.d_masks + t0);
         COUNT(1);
         g_eager_done[any_daily ? 1 : 0] = true;
         return;
@@ -678,7 +717,7 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(E.stream, cudaStreamCaptureModeThreadLocal));
         run_model_step(c, any_daily);
-        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, 0);
+        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, E.d_masks + t0);
         COUNT(1);
         CK(cudaStreamEndCapture(E.stream, &graph));
         CK(cudaGraphInstantiate(&sg.exec, graph, 0));
@@ -736,6 +775,8 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         int month_idx;
     };
     std::vector<SavedDate> saved(per_step_sync ? run.size() : 0);
+    CK(cudaMemsetAsync(E.d_err, 0, (size_t)nt * TILE * sizeof(int), E.stream));  // sticky within this call (k_collect_err)
+    bool any_failed = false;
     CK(cudaEventRecord(E.ev0, E.stream));
     for (int s = 0; s < nsteps; s++) {
         bool any_daily = false;
@@ -756,14 +797,15 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
             }
         }
         if (readback) {
-            // error codes: read back at most once a day in batched mode (members that failed keep failing:
-            // a NaN/blown-up state never passes the check again unless it is NaN, which the reference also lets pass)
+            // error codes: read back at most once a day in batched mode; the device keeps the first non-zero code of
+            // every member and freezes a failed member for the rest of the call (k_collect_err)
             CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
             for (size_t q = 0; q < run.size(); q++) {
                 const int code = E.h_err[epos[q]];
                 if (code != 0 && err_out[idx[q]] == 0) {
                     err_out[idx[q]] = code;
+                    any_failed = true;
                     if (per_step_sync) ctl[q]->model = saved[q].d, ctl[q]->month_idx = saved[q].month_idx;
                 }
             }
@@ -777,6 +819,21 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     CK(cudaStreamSynchronize(E.stream));
     CK(cudaGetLastError());  // a rejected kernel launch is not reported by the synchronisation
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+    if (any_failed) {
+        // the device masks of the failed members were cleared: upload them again with the next call; in a multi-step call
+        // the host mirrors ran ahead of a member that stopped at its failing step -- take them from the device
+        E.cached_handles.clear();
+        if (!per_step_sync)
+            for (size_t q = 0; q < run.size(); q++)
+                if (err_out[idx[q]] != 0) {
+                    Member *m = member_of(run[q]);
+                    m->current_step = (int)get_slot_host(*m, SL_STEP);
+                    Datetime &d = ctl[q]->model;
+                    d.y = (int)get_slot_host(*m, SL_YEAR), d.mo = (int)get_slot_host(*m, SL_MONTH);
+                    d.d = (int)get_slot_host(*m, SL_DAY), d.h = (int)get_slot_host(*m, SL_HOUR);
+                    d.mi = (int)get_slot_host(*m, SL_MINUTE), ctl[q]->month_idx = (int)get_slot_host(*m, SL_MONTH_IDX);
+                }
+    }
     for (int i = 0; i < n; i++) failed += (err_out[i] != 0 && err_out[i] != -1) ? 1 : 0;
     return failed;
 }
@@ -842,21 +899,16 @@ static void s2g_member(Member &m) {  // prognostics.f90:125-154
     Ctx c = single_ctx(m);
     s2g_ctx(c);
 }
-static void s2g_ctx(const Ctx &c) {
+// uvspec + the 41 inverse transforms into scratch (no host synchronisation: the descriptor list is resident)
+static void s2g_transforms(const Ctx &c) {
     const ScratchLayout &L = E.L;
     launch_uvspec(E.stream, c, E.off[V_vor], E.off[V_div], REF_SCR | L.ucos, REF_SCR | L.vcos, KX, 0);
     COUNT(1);
-    std::vector<InvDesc> v;
-    for (int k = 0; k < KX; k++) {
-        v.push_back(InvDesc{REF_SCR | (L.ucos + (long long)k * NSP), L.ug + (long long)k * NG, 2, 0});
-        v.push_back(InvDesc{REF_SCR | (L.vcos + (long long)k * NSP), L.vg + (long long)k * NG, 2, 0});
-        v.push_back(InvDesc{E.off[V_t] + (long long)k * NSP, L.tg + (long long)k * NG, 1, 0});
-        v.push_back(InvDesc{E.off[V_tr] + (long long)k * NSP, L.trg + (long long)k * NG, 1, 0});
-        v.push_back(InvDesc{E.off[V_phi] + (long long)k * NSP, L.pphig + (long long)k * NG, 1, 0});
-    }
-    v.push_back(InvDesc{E.off[V_ps], L.pslg, 1, 0});
-    run_inverse_list(c, v);
-    k_s2g_finish<<<dim3(NG / 4, c.ntiles), 128, 0, E.stream>>>(c, L);
+    run_inverse(c, E.d_inv_s2g, 5 * KX + 1);
+}
+static void s2g_ctx(const Ctx &c) {
+    s2g_transforms(c);
+    k_s2g_finish<<<dim3(NG / 4, c.ntiles), 128, 0, E.stream>>>(c, E.L);
     COUNT(1);
     CK(cudaStreamSynchronize(E.stream));
 }
@@ -955,18 +1007,26 @@ using namespace spdy;
 extern "C" {
 
 int spdy_set_device(int ordinal) {
+    API_LOCK;
     if (E.ready) return -1;
     E.device = ordinal;
     return 0;
 }
+int spdy_device_count(void) {
+    API_LOCK;
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 int spdy_synchronize(void) {
+    API_LOCK;
     if (E.ready) CK(cudaStreamSynchronize(E.stream));
     return 0;
 }
-float spdy_last_elapsed_ms(void) { return E.last_ms; }
-long long spdy_kernel_launches(void) { return g_launches; }
+float spdy_last_elapsed_ms(void) { API_LOCK; return E.last_ms; }
+long long spdy_kernel_launches(void) { API_LOCK; return g_launches; }
 
 int spdy_get_model_datetime(int64_t h, int *out) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     const int s[5] = {SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE};
@@ -975,12 +1035,14 @@ int spdy_get_model_datetime(int64_t h, int *out) {
 }
 
 int spdy_reserve(int n_members) {
+    API_LOCK;
     engine_init();
     ensure_state_tiles((n_members + TILE - 1) / TILE);
     return 0;
 }
 
 int64_t spdy_modelstate_init(void) {
+    API_LOCK;
     engine_init();
     int idx;
     if (!E.free_members.empty()) {
@@ -1008,6 +1070,7 @@ int64_t spdy_modelstate_init(void) {
 }
 
 void spdy_modelstate_init_sst_anom(int64_t h, int n_months) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m || n_months < 0) return;
     ensure_sst_months(n_months + 2);
@@ -1018,6 +1081,7 @@ void spdy_modelstate_init_sst_anom(int64_t h, int n_months) {
 }
 
 void spdy_modelstate_close(int64_t h) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return;
     m->alive = false;
@@ -1027,47 +1091,72 @@ void spdy_modelstate_close(int64_t h) {
 }
 
 int64_t spdy_create_datetime(int y, int mo, int d, int h, int mi) {
+    API_LOCK;
+    if (!E.free_dates.empty()) {  // closed containers are recycled (the reference deallocates them, .j2:204-210)
+        const int idx = E.free_dates.back();
+        E.free_dates.pop_back();
+        E.dates[idx] = Datetime{y, mo, d, h, mi, true};
+        return (int64_t)idx + 1;
+    }
     E.dates.push_back(Datetime{y, mo, d, h, mi, true});
     return (int64_t)E.dates.size();
 }
 void spdy_get_datetime(int64_t h, int *o) {
+    API_LOCK;
     if (h < 1 || h > (int64_t)E.dates.size()) return;
     const Datetime &d = E.dates[h - 1];
     o[0] = d.y, o[1] = d.mo, o[2] = d.d, o[3] = d.h, o[4] = d.mi;
 }
 void spdy_close_datetime(int64_t h) {
-    if (h >= 1 && h <= (int64_t)E.dates.size()) E.dates[h - 1].alive = false;
+    API_LOCK;
+    if (h >= 1 && h <= (int64_t)E.dates.size() && E.dates[h - 1].alive) {
+        E.dates[h - 1].alive = false;
+        E.free_dates.push_back((int)h - 1);
+    }
 }
 int64_t spdy_controlparams_init(int64_t s, int64_t e) {
+    API_LOCK;
     if (s < 1 || s > (int64_t)E.dates.size() || e < 1 || e > (int64_t)E.dates.size()) return 0;
     Control c;
     c.start = E.dates[s - 1], c.end = E.dates[e - 1], c.model = c.start, c.month_idx = 1, c.alive = true, c.bound_member = -1;
+    if (!E.free_controls.empty()) {
+        const int idx = E.free_controls.back();
+        E.free_controls.pop_back();
+        E.controls[idx] = c;
+        return (int64_t)idx + 1;
+    }
     E.controls.push_back(c);
     return (int64_t)E.controls.size();
 }
 void spdy_controlparams_close(int64_t h) {
+    API_LOCK;
     Control *c = control_of(h);
     if (!c) return;
     c->alive = false;
     if (c->bound_member >= 0 && c->bound_member < (int)E.members.size()) E.members[c->bound_member].bound_ctl = -1;
+    E.free_controls.push_back((int)h - 1);
 }
 
 int spdy_init(int64_t sh, int64_t ch) {
+    API_LOCK;
     Member *m = member_of(sh);
     Control *c = control_of(ch);
     if (!m || !c) return -1;
     return init_member(*m, *c);
 }
 int spdy_step(int64_t sh, int64_t ch) {
+    API_LOCK;
     int err = 0;
     step_members(&sh, &ch, 1, 1, &err, true);
     return err;
 }
-void spdy_parallel_step(const int64_t *s, const int64_t *c, int *err, int n) { step_members(s, c, n, 1, err, true); }
+void spdy_parallel_step(const int64_t *s, const int64_t *c, int *err, int n) { API_LOCK; step_members(s, c, n, 1, err, true); }
 int spdy_run_steps(const int64_t *s, const int64_t *c, int n, int nsteps, int *err) {
+    API_LOCK;
     return step_members(s, c, n, nsteps, err, false);
 }
 int spdy_check(int64_t h) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     Ctx c = single_ctx(*m);
@@ -1077,19 +1166,23 @@ int spdy_check(int64_t h) {
     return (int)get_slot_host(*m, SL_ERR);
 }
 void spdy_transform_spectral2grid(int64_t h) {
+    API_LOCK;
     Member *m = member_of(h);
     if (m) s2g_member(*m);
 }
 void spdy_transform_grid2spectral(int64_t h) {
+    API_LOCK;
     Member *m = member_of(h);
     if (m) g2s_member(*m);
 }
 void spdy_apply_grid_filter(int64_t h) {
+    API_LOCK;
     Member *m = member_of(h);
     if (m) filter_member(*m);
 }
 
 int spdy_shape(int64_t h, int v, int *dims, int *ndim) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m || v < 0 || v >= SPDY_NVARS) return -1;
     const spdy_vardef &d = SPDY_VARDEFS[v];
@@ -1099,6 +1192,7 @@ int spdy_shape(int64_t h, int v, int *dims, int *ndim) {
     return 0;
 }
 int spdy_get(int64_t h, int v, void *dst, size_t bytes) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m || v < 0 || v >= SPDY_NVARS) return -1;
     const spdy_vardef &d = SPDY_VARDEFS[v];
@@ -1126,6 +1220,7 @@ int spdy_get(int64_t h, int v, void *dst, size_t bytes) {
     return 0;
 }
 int spdy_set(int64_t h, int v, const void *src, size_t bytes) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m || v < 0 || v >= SPDY_NVARS) return -1;
     const spdy_vardef &d = SPDY_VARDEFS[v];
@@ -1159,6 +1254,7 @@ int spdy_set(int64_t h, int v, const void *src, size_t bytes) {
 }
 
 int spdy_debug_get_corh(int64_t h, double *tcorh, double *qcorh) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     const int nb = (NSP + 255) / 256;
@@ -1172,6 +1268,7 @@ int spdy_debug_get_corh(int64_t h, double *tcorh, double *qcorh) {
 }
 
 int spdy_debug_raw_step(int64_t h, int j1, int j2, int dt_kind) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     Ctx c = single_ctx(*m);
@@ -1185,6 +1282,7 @@ int spdy_debug_raw_step(int64_t h, int j1, int j2, int dt_kind) {
 // (31,32,8) complex each, psdt (31,32), trdt (31,32,8); the prognostic state is not advanced (physics diagnostics
 // are updated exactly as a model step would)
 int spdy_debug_tendencies(int64_t h, int j2, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     Ctx c = single_ctx(*m);
@@ -1211,6 +1309,7 @@ int spdy_debug_tendencies(int64_t h, int j2, double *vordt, double *divdt, doubl
 int spdy_debug_physics(int64_t h, const double *ug8, const double *vg8, const double *tg, const double *qg,
                        const double *phig, const double *pslg, double *utend8, double *vtend8, double *ttend,
                        double *qtend, int *dbg) {
+    API_LOCK;
     Member *m = member_of(h);
     if (!m) return -1;
     const ScratchLayout &L = E.L;
@@ -1245,6 +1344,7 @@ int spdy_debug_physics(int64_t h, const double *ug8, const double *vg8, const do
 }
 
 int spdy_table(const char *name, double *dst, int cap) {
+    API_LOCK;
     // host-only: the tables are built with glibc on the CPU and need no device (tables.cu)
     static ConstTables *hc = nullptr;
     static GlobTables *hg = nullptr;
@@ -1326,3 +1426,4 @@ int spdy_table(const char *name, double *dst, int cap) {
 }  // extern "C"
 
 #include "batch.cu"
+#include "ensemble.cu"

@@ -113,9 +113,14 @@ class Dataset:
                 f.createDimension(d, n)
             for d in sizes:
                 if d == "time":
+                    # whole days since t0 as int32 when every output time allows it (the encoding xarray picks for the
+                    # reference's daily fixtures), else minutes: sub-daily outputs (ModelCheckpoint(interval < 36))
+                    # keep distinct time values
+                    secs = [int((t - t0).total_seconds()) for t in self.coords["time"]]
+                    unit, div = ("days", 86400) if all(x % 86400 == 0 for x in secs) else ("minutes", 60)
                     v = f.createVariable("time", "i4", ("time",))
-                    v[:] = [int((t - t0).total_seconds() // 86400) for t in self.coords["time"]]
-                    v.units = "days since " + t0.strftime("%Y-%m-%d %H:%M:%S")
+                    v[:] = [x // div for x in secs]
+                    v.units = f"{unit} since " + t0.strftime("%Y-%m-%d %H:%M:%S")
                     v.calendar = "proleptic_gregorian"
                     v.axis = "T"
                     v.standard_name = "time"
@@ -141,10 +146,11 @@ class Dataset:
                 data = np.array(v.data, dtype=v.data.dtype.newbyteorder("="))
                 if name in f.dimensions:
                     if name == "time":
-                        base = datetime.strptime(v.units.decode().replace("days since ", ""), "%Y-%m-%d %H:%M:%S")
                         from datetime import timedelta
 
-                        coords[name] = [base + timedelta(days=int(x)) for x in data]
+                        unit, _, base = v.units.decode().partition(" since ")
+                        base = datetime.strptime(base, "%Y-%m-%d %H:%M:%S")
+                        coords[name] = [base + timedelta(**{unit: int(x)}) for x in data]
                     elif name == "ens":
                         coords[name] = [int(x) for x in data]
                     else:

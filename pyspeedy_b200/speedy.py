@@ -8,10 +8,13 @@ Differences, all forced by this image (no xarray / netCDF4 / HDF5) and documente
     array);
   * ``to_dataframe`` returns ``xarray.Dataset`` when xarray is importable, else :class:`pyspeedy_b200.dataset.Dataset`
     (same dims/ordering/dtypes, NetCDF-3 writer).
-Ensemble extension: ``SpeedyEns.run(..., steps_per_call=n)`` advances all members ``n`` steps per driver call.
+Ensemble extensions: ``SpeedyEns.run(..., steps_per_call=n)`` advances all members ``n`` steps per driver call;
+``SpeedyEns(n, comm=distributed.init())`` shards the members over one process per GPU; ``to_dataframe``, ``check`` and
+``mean_and_spread`` of an ensemble are single batched driver calls.
 """
 import json
 import os
+import warnings
 from datetime import datetime, timedelta
 
 import numpy as np
@@ -76,6 +79,7 @@ class Speedy:
             _speedy.controlparams_close(self._control_cnt)
             self._dealloc_date(self._start_date)
             self._dealloc_date(self._end_date)
+            self._dealloc_date(self._model_date)
         except Exception:  # interpreter shutdown
             pass
 
@@ -84,8 +88,9 @@ class Speedy:
         self.end_date = end_date
         if self.start_date > self.end_date:
             raise ValueError("The start date should be lower than the en date.")
+        if self._control_cnt is not None:
+            _speedy.controlparams_close(self._control_cnt)
         self._control_cnt = _speedy.controlparams_init(self._start_date, self._end_date)
-        self._model_date = None
         self.current_date = start_date
         self.n_months = (
             (self.end_date.year - self.start_date.year) * 12 + (self.end_date.month - self.start_date.month) + 1
@@ -133,12 +138,13 @@ class Speedy:
 
     @staticmethod
     def _set_fortran_date(container, date_value):
-        Speedy._dealloc_date(container)
-        if isinstance(date_value, datetime):
-            return _speedy.create_datetime(
-                date_value.year, date_value.month, date_value.day, date_value.hour, date_value.minute
-            )
-        raise TypeError("The input value is not a datetime object.")
+        if not isinstance(date_value, datetime):
+            raise TypeError("The input value is not a datetime object.")
+        ymdhm = (date_value.year, date_value.month, date_value.day, date_value.hour, date_value.minute)
+        if container is not None:  # same container, new value (the reference frees and re-creates it)
+            _speedy.set_datetime(container, *ymdhm)
+            return container
+        return _speedy.create_datetime(*ymdhm)
 
     def get_current_step(self):
         return self["current_step"]
@@ -200,7 +206,13 @@ class Speedy:
         if sst_anomaly is None and os.path.isfile(example_sst_anomaly_file()):
             sst_anomaly = example_sst_anomaly_file()
         if sst_anomaly is None:
-            ssta = np.zeros((96, 48, expected_months))  # documented deviation: default anomaly file unavailable
+            # documented deviation: the reference raises when its packaged sst_anomaly.nc is missing
+            # (pyspeedy/speedy.py:319-326); that file is not redistributable here, so the default is a ZERO anomaly
+            warnings.warn(
+                "pyspeedy_b200: the default SST anomaly file is not packaged; running with a zero SST anomaly. "
+                "Pass sst_anomaly=<array or .npz> to reproduce a reference run that used pyspeedy/data/sst_anomaly.nc.",
+                RuntimeWarning, stacklevel=3)
+            ssta = np.zeros((96, 48, expected_months))
         elif isinstance(sst_anomaly, str):
             if not os.path.isfile(sst_anomaly):
                 raise RuntimeError("The SST anomaly file does not exist.\n" f"File: {sst_anomaly}")
@@ -283,11 +295,18 @@ class Speedy:
 
 
 class SpeedyEns:
-    """Ensemble of Speedy model instances, advanced together by one driver call per step."""
+    """Ensemble of Speedy model instances, advanced together by one driver call per step.
 
-    def __init__(self, num_of_members, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2)):
-        self.n_members = num_of_members
-        self.members = [Speedy(start_date=start_date, end_date=end_date, member=n) for n in range(num_of_members)]
+    ``comm`` (extension, :mod:`pyspeedy_b200.distributed`): with one process per GPU, ``num_of_members`` is the size of
+    the WHOLE ensemble and this process creates only its own contiguous block (``member_id`` = global member number);
+    nothing is exchanged inside a time step, ``mean_and_spread`` is reduced over all ranks."""
+
+    def __init__(self, num_of_members, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2), comm=None):
+        self.comm = comm
+        self.n_total = num_of_members
+        first, count = comm.shard(num_of_members) if comm is not None else (0, num_of_members)
+        self.n_members = count
+        self.members = [Speedy(start_date=start_date, end_date=end_date, member=first + n) for n in range(count)]
         self.current_date = self.members[0].current_date
 
     def __iter__(self):
@@ -302,19 +321,61 @@ class SpeedyEns:
         self.current_date = start_date
 
     def to_dataframe(self, variables=None):
-        return Dataset.merge([member.to_dataframe(variables=variables) for member in self])
+        """Dataset with the current state of every member: dims (time, ens, lev, lat, lon), float32, levels increasing
+        with height -- what merging the members' ``to_dataframe`` gives (pyspeedy/speedy.py:538-545), built from ONE
+        batched spectral2grid and ONE device gather + copy per variable (cast to float32 on the device)."""
+        if variables is None:
+            variables = DEFAULT_OUTPUT_VARS
+        s, _ = self.handles()
+        _speedy.batch_spectral2grid(s)
+        data_vars, attrs = dict(), dict()
+        for var in variables:
+            e = MODEL_STATE_DEF[var]
+            nc_dims = list(e["nc_dims"])  # e.g. (lon, lat, lev): Fortran order == reversed C order of the gather
+            a = _speedy.ensemble_get(s, var, dtype=np.float32)  # (ens, lev, lat, lon)
+            dims = ["ens"] + nc_dims[::-1]
+            if "lev" in dims:
+                a = np.flip(a, axis=dims.index("lev"))
+            order = [d for d in ("time", "ens", "lev", "lat", "lon") if d in dims or d == "time"]
+            a = np.transpose(a[None], [(["time"] + dims).index(d) for d in order])
+            name = e["alt_name"]
+            data_vars[name] = (order, a)
+            attrs[name] = dict(long_name=e["desc"], standard_name=e["std_name"])
+            if e["units"] is not None:
+                attrs[name]["units"] = e["units"]
+        m0 = self.members[0]
+        coords = dict(lon=m0["lon"], lat=m0["lat"], lev=m0["lev"][::-1], time=[self.current_date],
+                      ens=[m.member_id for m in self])
+        ds = Dataset(data_vars=data_vars, coords=coords, attrs=attrs)
+        return ds.to_xarray() if Dataset.HAVE_XARRAY else ds
+
+    def check(self):
+        """``Speedy.check`` for every member with one driver call; raises like the per-member loop of
+        pyspeedy/callbacks.py:103-111 would at the first failing member."""
+        s, _ = self.handles()
+        codes = _speedy.batch_check(s)
+        if (codes < 0).any():
+            raise RuntimeError(ERROR_CODES[int(codes[codes < 0][0])])
 
     # ---- ensemble extensions (no reference counterpart) -----------------------------------------------------
     def handles(self):
-        s = np.array([m._state_cnt for m in self], dtype=np.int64)  # noqa
-        c = np.array([m._control_cnt for m in self], dtype=np.int64)  # noqa
+        if getattr(self, "_handles", None) is None or len(self._handles[0]) != len(self.members):
+            s = np.array([m._state_cnt for m in self], dtype=np.int64)  # noqa
+            c = np.array([m._control_cnt for m in self], dtype=np.int64)  # noqa
+            self._handles = (s, c)
+        s, c = self._handles
+        if any(int(c[i]) != m._control_cnt for i, m in ((0, self.members[0]), (-1, self.members[-1]))):  # set_params
+            self._handles = None
+            return self.handles()
         return s, c
 
     def set_bc(self, bc_file=None, sst_anomaly=None, perturb_sigma=None, seed=1234):
         """Initialise every member with the same boundary conditions: member 0 runs the full ``Speedy.set_bc`` and
         its device state is cloned into the others (identical to calling ``set_bc`` per member, which is how the
         reference does it, but one initialisation instead of N).  ``perturb_sigma`` adds the i.i.d. N(0, sigma)
-        grid-point temperature perturbation of examples/Ensemble_forecast.ipynb to every member."""
+        grid-point temperature perturbation of examples/Ensemble_forecast.ipynb to every member (counter-based
+        generator keyed by the member's slot, so every rank of a sharded ensemble needs its own ``seed``; the
+        default adds the rank)."""
         self.members[0].set_bc(bc_file=bc_file, sst_anomaly=sst_anomaly)
         s, _ = self.handles()
         if len(s) > 1:
@@ -322,22 +383,25 @@ class SpeedyEns:
         for m in self.members[1:]:
             m._initialized_bc = m._initialized_ssta = True
         if perturb_sigma:
-            _speedy.perturb_temperature(s, seed, perturb_sigma)
+            _speedy.perturb_temperature(s, seed + (self.comm.rank if self.comm is not None else 0), perturb_sigma)
 
     def mean_and_spread(self, variables=None):
-        """Ensemble mean and spread (std, ddof=0) of grid variables; the sums are reduced on the device."""
+        """Ensemble mean and spread (std, ddof=0) of grid variables over ALL members (all ranks), as
+        {var: (mean, spread)}.  The six default outputs come from the fused path (sums in the epilogue of the batched
+        spectral2grid, one NCCL all-reduce, one copy); other variables from per-variable device reductions."""
         if variables is None:
             variables = DEFAULT_OUTPUT_VARS
         s, _ = self.handles()
-        _speedy.batch_spectral2grid(s)
         out = {}
+        fused = _speedy.ensemble_mean_spread(s, self.n_total)  # also brings the *_grid variables up to date
         for v in variables:
-            shift = self.members[0][v]
-            s1, s2 = _speedy.ensemble_sums(s, v, shift=shift)
-            n = float(self.n_members)
-            mean = s1 / n
-            var = np.maximum(s2 / n - (mean - shift) ** 2, 0.0)
-            out[v] = (mean, np.sqrt(var))
+            if v in fused:
+                out[v] = fused[v]
+                continue
+            from pyspeedy_b200.distributed import mean_spread_from_sums
+
+            s1, s2 = _speedy.ensemble_sums(s, v)
+            out[v] = mean_spread_from_sums(s1, s2, self.n_total)
         return out
 
     def run(self, callbacks=None, steps_per_call=1):
@@ -348,11 +412,8 @@ class SpeedyEns:
             callbacks = []
         end_date = self.members[0].end_date
         dt_step = timedelta(seconds=3600 * 24 / 36)
-        state_cnts = np.zeros(self.n_members, dtype=np.int64)
-        control_cnts = np.zeros(self.n_members, dtype=np.int64)
-        for m, member in enumerate(self):
-            state_cnts[m] = member._state_cnt  # noqa
-            control_cnts[m] = member._control_cnt  # noqa
+        state_cnts, control_cnts = self.handles()
+        date_cnts = np.array([m._model_date for m in self], dtype=np.int64)  # noqa
         while self.current_date < end_date:
             if steps_per_call > 1:
                 left = int(round((end_date - self.current_date) / dt_step))
@@ -367,8 +428,9 @@ class SpeedyEns:
                 for n, code in enumerate(error_codes):
                     msg += f"Member{n}: {ERROR_CODES[code]}\n"
                 raise RuntimeError(msg)
-            for member in self:
-                member.current_date = self.current_date
+            # "update current date in all members" (pyspeedy/speedy.py:588-590): one driver call, the members' datetime
+            # containers are updated in place
+            _speedy.set_datetimes(date_cnts, self.current_date)
             for callback in callbacks:
                 callback(self)
 
