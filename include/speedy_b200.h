@@ -116,6 +116,17 @@ int spdy_batch_legendre_inv(const double *spec, double *four /* n x (62,48) */, 
 int spdy_batch_legendre_dir(const double *four, double *spec, int n);
 int spdy_batch_fourier_inv(const double *four, double *grid, int kcos, int n);
 int spdy_batch_fourier_dir(const double *grid, double *four, int n);
+/* spectral operators on batches of (31,32) complex fields, through the kernels of the model step (operator-level parity):
+ * vort2vel = uvspec (spectral.f90:190-214), vel2vort = vdspec (:160-186), gradient (:275-296), laplacian / laplacian_inv
+ * (:140-155), grid_vel2vort (:218-248; kcos = 2: cosgr, else cosgr2) */
+int spdy_batch_vort2vel(const double *vor, const double *div, double *ucos, double *vcos, int n);
+int spdy_batch_vel2vort(const double *ucos, const double *vcos, double *vor, double *div, int n);
+int spdy_batch_gradient(const double *psi, double *dx, double *dy, int n);
+int spdy_batch_laplacian(const double *in, double *out, int inverse, int n);
+int spdy_batch_grid_vel2vort(const double *ug, const double *vg, double *vor, double *div, int kcos, int n);
+/* BASELINE config 4: npairs synthetic (vor, div) pairs resident in HBM; one rep = vort2vel -> spec2grid(kcos 2) of the
+ * 2 npairs wind fields -> grid2spec (cos-latitude loader) -> vel2vort -> gradient; ms[6] = mean device ms per rep, then per stage */
+int spdy_bench_spectral_chain(const double *vor, const double *div, int npairs, int reps, float *ms);
 /* resident round trip for the spectral microbench: n synthetic fields stay in HBM, `reps` x (spec2grid, grid2spec);
  * returns average device ms per rep; per_kernel_ms[4] = legendre_inv, fft_inv, fft_fwd, legendre_dir */
 int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, float *ms_per_rep, float *per_kernel_ms);
@@ -128,6 +139,9 @@ int spdy_debug_raw_step(int64_t state, int j1, int j2, int dt_kind);
 int spdy_debug_get_corh(int64_t state, double *tcorh, double *qcorh);
 /* tendencies as returned by get_tendencies(state, ..., j2) (tendencies.f90:11-39); the prognostics are not advanced */
 int spdy_debug_tendencies(int64_t state, int j2, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt);
+/* stage 1: divdt, tdt, psdt as they enter implicit_terms (time_stepping.f90:71-75; vordt, trdt as in stage 2); stage 2: same as above */
+int spdy_debug_tendencies_stage(int64_t state, int j2, int stage, double *vordt, double *divdt, double *tdt, double *psdt,
+                                double *trdt);
 
 #ifdef __cplusplus
 }

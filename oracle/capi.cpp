@@ -333,6 +333,15 @@ void orc_tendencies(void *st, int j2, double *vordt, double *divdt, double *tdt,
                    S2{(cplx *)psdt, mx}, S3{(cplx *)trdt, mx, nx}, j2);
 }
 void orc_raw_step(void *st, int j1, int j2, double dt) { step(*(State *)st, j1, j2, dt); }
+// implicit_terms (implicit.f90:234-289) in place on (mx,nx,kx) divdt, tdt and (mx,nx) psdt, with the state's time step
+void orc_implicit_terms(void *st, double *divdt, double *tdt, double *psdt) {
+    ((State *)st)->imp.implicit_terms(S3{(cplx *)divdt, mx, nx}, S3{(cplx *)tdt, mx, nx}, S2{(cplx *)psdt, mx});
+}
+// horizontal diffusion + time integration of step() for GIVEN tendencies (time_stepping.f90:78-144); tendencies are clobbered
+void orc_apply_tendencies(void *st, int j1, double dt, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt) {
+    apply_tendencies(*(State *)st, j1, dt, S3{(cplx *)vordt, mx, nx}, S3{(cplx *)divdt, mx, nx}, S3{(cplx *)tdt, mx, nx},
+                     S2{(cplx *)psdt, mx}, S3{(cplx *)trdt, mx, nx});
+}
 void orc_set_time_step(void *st, double dt) { ((State *)st)->imp.set_time_step(dt); }
 void orc_set_forcing(void *st, void *ctl, int imode) {
     Control &c = *(Control *)ctl;

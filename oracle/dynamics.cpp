@@ -456,11 +456,18 @@ static void step_field_2d(const Spectral &sp, int j1, double dt, double eps, S2 
 
 // time_stepping.f90:38-147
 void step(State &s, int j1, int j2, double dt) {
-    const Spectral &sp = s.spec;
-    Implicit &im = s.imp;
-    Spec3 vordt, divdt, tdt, ctmp, trdt;
+    Spec3 vordt, divdt, tdt, trdt;
     Spec2 psdt;
     get_tendencies(s, vordt, divdt, tdt, psdt, trdt, j2);
+    apply_tendencies(s, j1, dt, vordt, divdt, tdt, psdt, trdt);
+}
+
+// time_stepping.f90:78-144: horizontal diffusion, stratospheric drag and the leapfrog / RAW time integration for given
+// tendencies (split off step() so that tests can feed tendencies in)
+void apply_tendencies(State &s, int j1, double dt, S3 vordt, S3 divdt, S3 tdt, S2 psdt, S3 trdt) {
+    const Spectral &sp = s.spec;
+    Implicit &im = s.imp;
+    Spec3 ctmp;
 
     S3 vor1 = s.s4lev(V_vor, 1), div1 = s.s4lev(V_div, 1), t1 = s.s4lev(V_t, 1), tr1 = s.s4lev(V_tr, 1);
     hdiff3(vor1, vordt, im.dmp, im.dmp1);
@@ -485,10 +492,10 @@ void step(State &s, int j1, int j2, double dt) {
     double eps = (j1 == 1) ? 0.0 : rob;
     step_field_2d(sp, j1, dt, eps, s.s3lev(V_ps, 1), s.s3lev(V_ps, 2), psdt);
     const int ids[4] = {V_vor, V_div, V_t, V_tr};
-    Spec3 *fd[4] = {&vordt, &divdt, &tdt, &trdt};
+    S3 fd[4] = {vordt, divdt, tdt, trdt};
     for (int q = 0; q < 4; q++)
         for (int k = 1; k <= kx; k++)
-            step_field_2d(sp, j1, dt, eps, s.s4lev(ids[q], 1).slab(k), s.s4lev(ids[q], 2).slab(k), fd[q]->slab(k));
+            step_field_2d(sp, j1, dt, eps, s.s4lev(ids[q], 1).slab(k), s.s4lev(ids[q], 2).slab(k), fd[q].slab(k));
 }
 
 // time_stepping.f90:13-27

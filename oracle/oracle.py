@@ -62,6 +62,8 @@ def lib():
         L.orc_get_corh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tendencies.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.orc_raw_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.orc_implicit_terms.argtypes = [C.c_void_p] * 4
+        L.orc_apply_tendencies.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 5
         L.orc_set_time_step.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_couple.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -292,6 +294,17 @@ class State:
         trdt = np.zeros((MX, NX, KX), dtype=np.complex128, order="F")
         lib().orc_tendencies(C.c_void_p(self.h), j2, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(psdt), _ptr(trdt))
         return dict(vordt=outs[0], divdt=outs[1], tdt=outs[2], psdt=psdt, trdt=trdt)
+
+    def implicit_terms(self, divdt, tdt, psdt):
+        """implicit.f90:234-289 applied to copies of the (31,32,8) / (31,32) complex tendencies; returns the corrected ones."""
+        out = [np.array(a, dtype=np.complex128, order="F", copy=True) for a in (divdt, tdt, psdt)]
+        lib().orc_implicit_terms(C.c_void_p(self.h), *[_ptr(a) for a in out])
+        return out
+
+    def apply_tendencies(self, j1, dt, vordt, divdt, tdt, psdt, trdt):
+        """Horizontal diffusion + leapfrog / RAW filter of time_stepping.f90:78-144 for given tendencies."""
+        t = [np.array(a, dtype=np.complex128, order="F", copy=True) for a in (vordt, divdt, tdt, psdt, trdt)]
+        lib().orc_apply_tendencies(C.c_void_p(self.h), j1, float(dt), *[_ptr(a) for a in t])
 
     def raw_step(self, j1, j2, dt):
         lib().orc_raw_step(C.c_void_p(self.h), j1, j2, float(dt))

@@ -263,6 +263,7 @@ void get_grid_point_tendencies(State &s, S3 vordt, S3 divdt, S3 tdt, S2 psdt, S3
 void get_spectral_tendencies(State &s, S3 divdt, S3 tdt, S2 psdt, int j2);
 void get_tendencies(State &s, S3 vordt, S3 divdt, S3 tdt, S2 psdt, S3 trdt, int j2);
 void step(State &s, int j1, int j2, double dt);
+void apply_tendencies(State &s, int j1, double dt, S3 vordt, S3 divdt, S3 tdt, S2 psdt, S3 trdt);
 void first_step(State &s);
 int check_diagnostics(State &s, int time_lev);
 

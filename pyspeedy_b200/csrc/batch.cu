@@ -11,11 +11,16 @@ struct Workspace {
     InvDesc *d_inv = nullptr;
     FwdDesc *d_fwd = nullptr;
     FwdOut *d_out = nullptr;
+    InvDesc *d_inv2 = nullptr;
+    FwdDesc *d_fwd2 = nullptr;
+    FwdOut *d_out2 = nullptr;
     double *d_lin = nullptr;
     size_t lin_cap = 0;
 };
 static Workspace W;
-constexpr long long WS_SPEC = 0, WS_FOUR = NSP, WS_GRID = NSP + NFOUR, WS_ELEMS = NSP + NFOUR + NG;
+// per pseudo-member: four spectral fields, one Fourier field, two grid fields
+constexpr long long WS_SPEC = 0, WS_SPEC2 = NSP, WS_SPEC3 = 2 * NSP, WS_SPEC4 = 3 * NSP, WS_FOUR = 4 * NSP,
+                    WS_GRID = 4 * NSP + NFOUR, WS_GRID2 = WS_GRID + NG, WS_ELEMS = WS_GRID2 + NG;
 
 static Ctx ws_ctx(int nfields) {
     engine_init();
@@ -41,6 +46,14 @@ static Ctx ws_ctx(int nfields) {
         const FwdOut o{REF_SCR | WS_SPEC};
         CK(cudaMemcpy(W.d_fwd, &f, sizeof(f), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(W.d_out, &o, sizeof(o), cudaMemcpyHostToDevice));
+        // two-field lists of the wind chain: (u cos, v cos) in WS_SPEC3/4 <-> (u, v) in WS_GRID/2
+        const InvDesc i2[2] = {InvDesc{REF_SCR | WS_SPEC3, WS_GRID, 2, 0}, InvDesc{REF_SCR | WS_SPEC4, WS_GRID2, 2, 0}};
+        const FwdOut o2[2] = {FwdOut{REF_SCR | WS_SPEC3}, FwdOut{REF_SCR | WS_SPEC4}};
+        CK(cudaMalloc(&W.d_inv2, sizeof(i2)));
+        CK(cudaMalloc(&W.d_fwd2, 2 * sizeof(FwdDesc)));
+        CK(cudaMalloc(&W.d_out2, sizeof(o2)));
+        CK(cudaMemcpy(W.d_inv2, i2, sizeof(i2), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(W.d_out2, o2, sizeof(o2), cudaMemcpyHostToDevice));
     }
     Ctx c = make_ctx(W.tiles, W.masks, nt);
     c.scr = W.buf, c.scr_elems = WS_ELEMS, c.st = nullptr;
@@ -145,6 +158,132 @@ int spdy_batch_grid2spec(const double *grid, double *spec, int n) {
     }
     COUNT(2);
     ws_move(nullptr, spec, WS_SPEC, NSP, n);
+    return 0;
+}
+
+// ---- spectral operators on batches of fields (operator-level parity tests): the kernels of the model step --------------
+static void ws_set_fwd2(int kcos) {  // forward list of the wind chain: u, v times cosgr (kcos 2) or cosgr2 (3), spectral.f90:229-242
+    const FwdDesc f2[2] = {FwdDesc{REF_SCR | WS_GRID, 0, 0.0, kcos, 0, FM_COS, 0}, FwdDesc{REF_SCR | WS_GRID2, 0, 0.0, kcos, 1, FM_COS, 0}};
+    CK(cudaMemcpy(W.d_fwd2, f2, sizeof(f2), cudaMemcpyHostToDevice));
+}
+static void ws_forward2(const Ctx &c) {  // (WS_GRID, WS_GRID2) -> (WS_SPEC3, WS_SPEC4) with the cos-latitude loader
+    if (fused_transforms()) {
+        launch_grid2spec_mma2(E.stream, c, FM_COS, W.d_fwd2, W.d_out2, 2, 0);
+        COUNT(1);
+    } else {
+        launch_fft_fwd(E.stream, c, FM_COS, W.d_fwd2, 2, WS_FOUR);  // Fourier slots 0, 1: the workspace has ONE Fourier field
+        launch_legendre_dir(E.stream, c, W.d_out2, 2, WS_FOUR);
+        COUNT(2);
+    }
+}
+// vort2vel = uvspec (spectral.f90:190-214): (vor, div) -> (u cos, v cos)
+int spdy_batch_vort2vel(const double *vor, const double *dv, double *u, double *v, int n) {
+    API_LOCK;
+    Ctx c = ws_ctx(n);
+    ws_move(vor, nullptr, WS_SPEC, NSP, n), ws_move(dv, nullptr, WS_SPEC2, NSP, n);
+    launch_uvspec(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, 1, 0);
+    COUNT(1);
+    ws_move(nullptr, u, WS_SPEC3, NSP, n), ws_move(nullptr, v, WS_SPEC4, NSP, n);
+    return 0;
+}
+// vel2vort = vdspec (spectral.f90:160-186): spectral (u, v) -> (vor, div)
+int spdy_batch_vel2vort(const double *u, const double *v, double *vor, double *dv, int n) {
+    API_LOCK;
+    Ctx c = ws_ctx(n);
+    ws_move(u, nullptr, WS_SPEC3, NSP, n), ws_move(v, nullptr, WS_SPEC4, NSP, n);
+    launch_vdspec(E.stream, c, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2);
+    COUNT(1);
+    ws_move(nullptr, vor, WS_SPEC, NSP, n), ws_move(nullptr, dv, WS_SPEC2, NSP, n);
+    return 0;
+}
+// gradient (spectral.f90:275-296)
+int spdy_batch_gradient(const double *psi, double *dx, double *dy, int n) {
+    API_LOCK;
+    Ctx c = ws_ctx(n);
+    ws_move(psi, nullptr, WS_SPEC, NSP, n);
+    launch_gradient(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, 0);
+    COUNT(1);
+    ws_move(nullptr, dx, WS_SPEC3, NSP, n), ws_move(nullptr, dy, WS_SPEC4, NSP, n);
+    return 0;
+}
+// laplacian / laplacian_inv (spectral.f90:140-155)
+int spdy_batch_laplacian(const double *in, double *out, int inverse, int n) {
+    API_LOCK;
+    Ctx c = ws_ctx(n);
+    ws_move(in, nullptr, WS_SPEC, NSP, n);
+    launch_laplacian(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2, inverse);
+    COUNT(1);
+    ws_move(nullptr, out, WS_SPEC2, NSP, n);
+    return 0;
+}
+// grid_vel2vort (spectral.f90:218-248): grid (u, v) x cosgr (kcos = 2) or cosgr2 -> two forward transforms -> vel2vort
+int spdy_batch_grid_vel2vort(const double *ug, const double *vg, double *vor, double *dv, int kcos, int n) {
+    API_LOCK;
+    Ctx c = ws_ctx(n);
+    ws_set_fwd2(kcos == 2 ? 2 : 3);
+    ws_move(ug, nullptr, WS_GRID, NG, n), ws_move(vg, nullptr, WS_GRID2, NG, n);
+    if (fused_transforms()) {
+        ws_forward2(c);
+    } else {  // one Fourier field per pseudo-member in the workspace: the two transforms one after the other
+        FwdDesc f = FwdDesc{REF_SCR | WS_GRID, 0, 0.0, kcos == 2 ? 2 : 3, 0, FM_COS, 0};
+        FwdOut o = FwdOut{REF_SCR | WS_SPEC3};
+        for (int q = 0; q < 2; q++) {
+            CK(cudaMemcpy(W.d_fwd2, &f, sizeof(f), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(W.d_out2, &o, sizeof(o), cudaMemcpyHostToDevice));
+            launch_fft_fwd(E.stream, c, FM_COS, W.d_fwd2, 1, WS_FOUR);
+            launch_legendre_dir(E.stream, c, W.d_out2, 1, WS_FOUR);
+            COUNT(2);
+            CK(cudaStreamSynchronize(E.stream));
+            f.a = REF_SCR | WS_GRID2, o.dst = REF_SCR | WS_SPEC4;
+        }
+        const FwdOut o2[2] = {FwdOut{REF_SCR | WS_SPEC3}, FwdOut{REF_SCR | WS_SPEC4}};
+        CK(cudaMemcpy(W.d_out2, o2, sizeof(o2), cudaMemcpyHostToDevice));
+    }
+    launch_vdspec(E.stream, c, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2);
+    COUNT(1);
+    ws_move(nullptr, vor, WS_SPEC, NSP, n), ws_move(nullptr, dv, WS_SPEC2, NSP, n);
+    return 0;
+}
+
+// BASELINE config 4: `npairs` synthetic (vor, div) pairs resident in HBM; one rep =
+//   vort2vel -> spec2grid (kcos = 2) of the 2*npairs wind fields -> grid2spec with the cos-latitude loader -> vel2vort ->
+//   gradient(vor): the grid<->spectral round trip with the grad / uvspec / vdspec chain, through the kernels of the model
+//   step (fused transforms).  The output (vor, div) of a rep is the input of the next (the chain is a projection up to the
+//   reference's 4e-3 quadrature error, so the fields stay bounded).  ms[0] = mean device time per rep, ms[1..5] = per stage.
+int spdy_bench_spectral_chain(const double *vor, const double *dv, int npairs, int reps, float *ms) {
+    API_LOCK;
+    if (!fused_transforms()) {
+        fprintf(stderr, "speedy-b200: spdy_bench_spectral_chain times the fused transforms (unset SPDY_FUSED)\n");
+        return -1;
+    }
+    Ctx c = ws_ctx(npairs);
+    ws_set_fwd2(2);
+    ws_move(vor, nullptr, WS_SPEC, NSP, npairs), ws_move(dv, nullptr, WS_SPEC2, NSP, npairs);
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
+    float acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = -3; r < reps; r++) {  // three warm-up reps
+        CK(cudaEventRecord(ev[0], E.stream));
+        launch_uvspec(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, 1, 0);
+        CK(cudaEventRecord(ev[1], E.stream));
+        launch_spec2grid_mma3(E.stream, c, W.d_inv2, 2);
+        CK(cudaEventRecord(ev[2], E.stream));
+        ws_forward2(c);
+        CK(cudaEventRecord(ev[3], E.stream));
+        launch_vdspec(E.stream, c, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2);
+        CK(cudaEventRecord(ev[4], E.stream));
+        launch_gradient(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, 0);
+        CK(cudaEventRecord(ev[5], E.stream));
+        COUNT(5);
+        CK(cudaStreamSynchronize(E.stream));
+        if (r >= 0) {
+            float t;
+            for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1])), acc[i + 1] += t;
+            CK(cudaEventElapsedTime(&t, ev[0], ev[5]));
+            acc[0] += t;
+        }
+    }
+    for (int i = 0; i < 6; i++) CK(cudaEventDestroy(ev[i])), ms[i] = reps > 0 ? acc[i] / reps : 0.f;
     return 0;
 }
 

@@ -310,6 +310,15 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
         const double g = phi[k * lev] + (D_RGAS * c_T.tref[k]) * ps1;
         divdt[k] = divdt[k] - ((-g) * el2);
     }
+    if (dump >= 0 && j1 < 0) {  // test hook, stage 1 (j1 = -1): divdt, tdt, psdt BEFORE the implicit correction, i.e. the
+#pragma unroll              // operands implicit_terms receives (time_stepping.f90:71-75)
+        for (int k = 0; k < KX; k++) {
+            *(scp(c, t, dump + (long long)(8 + k) * NSP, lane) + e) = divdt[k];
+            *(scp(c, t, dump + (long long)(16 + k) * NSP, lane) + e) = tdt[k];
+        }
+        *(scp(c, t, dump + 24ll * NSP, lane) + e) = psdt;
+        return;
+    }
     // ---- C. semi-implicit correction (implicit.f90:234-289)
     {
         double yf[KX];
@@ -476,6 +485,34 @@ __device__ __forceinline__ void advance_calendar(const Ctx &c, int t, int lane) 
 __global__ void k_update_forcing_params(const Ctx c) {
     const int lane = threadIdx.x, t = blockIdx.x;
     if (lane_active(c, t, lane)) update_forcing_params(c, t, lane);
+}
+
+// ---- stand-alone spectral operators for the operator-level entry points (spdy_batch_vel2vort, spdy_batch_laplacian) ----
+// vel2vort (spectral.f90:160-186) through the very device function the spectral step uses (vdspec_comp), one component
+// per thread
+__global__ void __launch_bounds__(128) k_vdspec(const Ctx c, FieldRef u, FieldRef v, FieldRef vor, FieldRef dv) {
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    const int cc = w & 1, q = w >> 1;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const size_t e = (size_t)(2 * m + cc + M2 * n) * TILE;
+    double vo, d;
+    vdspec_comp<3>(c.G->gradx[m], c.G->vddym[q], c.G->vddyp[q], refp(c, t, u, lane) + e, refp(c, t, v, lane) + e, n, cc, vo, d);
+    *(refp(c, t, vor, lane) + e) = vo, *(refp(c, t, dv, lane) + e) = d;
+}
+// laplacian / laplacian_inv (spectral.f90:140-155) in the form the step evaluates them: -(x) * el2, -(x) * elm2
+__global__ void __launch_bounds__(128) k_laplacian(const Ctx c, FieldRef in, FieldRef out, int inverse) {
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    const int cc = w & 1, q = w >> 1;
+    if (q >= NSPC) return;
+    const size_t e = (size_t)(2 * (q % MX) + cc + M2 * (q / MX)) * TILE;
+    *(refp(c, t, out, lane) + e) = (-*(refp(c, t, in, lane) + e)) * (inverse ? c.G->elm2[q] : c.G->el2[q]);
+}
+void launch_vdspec(cudaStream_t s, const Ctx &c, FieldRef u, FieldRef v, FieldRef vor, FieldRef dv) {
+    k_vdspec<<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, u, v, vor, dv);
+}
+void launch_laplacian(cudaStream_t s, const Ctx &c, FieldRef in, FieldRef out, int inverse) {
+    k_laplacian<<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, in, out, inverse);
 }
 
 void launch_grid_dyn(cudaStream_t s, const Ctx &c, const ScratchLayout &L) {

@@ -583,6 +583,7 @@ static void run_forcing(const Ctx &c, int imode) {
     COUNT(4);
 }
 
+static int g_dump_stage = 2;  // tendency dump: 1 = before implicit_terms, 2 = as returned by get_tendencies
 // step(j1, j2, dt) of time_stepping.f90:38-147: tendencies + diffusion + time integration
 static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, int impl_idx, long long dump = -1) {
     const ScratchLayout &L = E.L;
@@ -610,7 +611,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
         COUNT(2);
     }
     run_forward_lists(c, E.d_fwd, E.n_fwd, E.d_out, FW_COUNT, dump < 0 ? 1 : 0);  // the tendency dump reads every row
-    launch_spec_step(E.stream, c, L, j1, dt, eps, impl_idx, dump);
+    launch_spec_step(E.stream, c, L, (dump >= 0 && g_dump_stage == 1) ? -1 : j1, dt, eps, impl_idx, dump);
     prof_mark(E.stream, PC_SPEC_STEP);
     COUNT(2);  // k_spec_step_vq + k_spec_step_dt
 }
@@ -1281,13 +1282,23 @@ int spdy_debug_raw_step(int64_t h, int j1, int j2, int dt_kind) {
 // tendencies of one member as returned by get_tendencies(state, ..., j2) (tendencies.f90:11-39): vordt, divdt, tdt
 // (31,32,8) complex each, psdt (31,32), trdt (31,32,8); the prognostic state is not advanced (physics diagnostics
 // are updated exactly as a model step would)
+int spdy_debug_tendencies_stage(int64_t h, int j2, int stage, double *vordt, double *divdt, double *tdt, double *psdt,
+                                double *trdt);
 int spdy_debug_tendencies(int64_t h, int j2, double *vordt, double *divdt, double *tdt, double *psdt, double *trdt) {
+    return spdy_debug_tendencies_stage(h, j2, 2, vordt, divdt, tdt, psdt, trdt);
+}
+// stage 1: divdt, tdt, psdt as they ENTER implicit_terms (time_stepping.f90:71-75), i.e. after get_grid_point_tendencies and
+// get_spectral_tendencies; stage 2: as returned by get_tendencies (after the semi-implicit correction)
+int spdy_debug_tendencies_stage(int64_t h, int j2, int stage, double *vordt, double *divdt, double *tdt, double *psdt,
+                                double *trdt) {
     API_LOCK;
     Member *m = member_of(h);
-    if (!m) return -1;
+    if (!m || stage < 1 || stage > 2) return -1;
     Ctx c = single_ctx(*m);
     const long long dump = E.L.four;
+    g_dump_stage = stage;
     run_step_core(c, 2, j2, 2.0 * H_DELT, FL(0.05), 2, dump);
+    g_dump_stage = 2;
     CK(cudaStreamSynchronize(E.stream));
     auto down = [&](double *dst, long long off, long long n) {
         for (long long o = 0; o < n; o += (long long)E.stage_elems) {

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    # Speedy.set_bc() without sst_anomaly= warns that the reference's default anomaly file is not packaged (zero anomaly)
+    config.addinivalue_line("filterwarnings", "ignore:pyspeedy_b200. the default SST anomaly file:RuntimeWarning")
 
 
 @pytest.fixture(scope="session")
