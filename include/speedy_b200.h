@@ -127,6 +127,10 @@ int spdy_batch_grid_vel2vort(const double *ug, const double *vg, double *vor, do
 /* BASELINE config 4: npairs synthetic (vor, div) pairs resident in HBM; one rep = vort2vel -> spec2grid(kcos 2) of the
  * 2 npairs wind fields -> grid2spec (cos-latitude loader) -> vel2vort -> gradient; ms[6] = mean device ms per rep, then per stage */
 int spdy_bench_spectral_chain(const double *vor, const double *div, int npairs, int reps, float *ms);
+/* BASELINE config 5: the column physics alone on synthetic columns; sets = nsets x 45 x (96,48) doubles (ug8, vg8, pslg,
+ * utend8, vtend8, then tg, qg, phig, ttend, qtend with 8 levels each); member i works on set i % nsets; ms[2] = mean device ms
+ * of a short-wave step and of a long-wave-only step */
+int spdy_bench_physics(const int64_t *states, int n, const double *sets, int nsets, int reps, float *ms);
 /* resident round trip for the spectral microbench: n synthetic fields stay in HBM, `reps` x (spec2grid, grid2spec);
  * returns average device ms per rep; per_kernel_ms[4] = legendre_inv, fft_inv, fft_fwd, legendre_dir */
 int spdy_bench_roundtrip(const double *spec, double *spec_out, int n, int reps, float *ms_per_rep, float *per_kernel_ms);

@@ -84,6 +84,14 @@ def lib():
         L.spdy_batch_fourier_inv.argtypes = [vp, vp, ci, ci]
         L.spdy_batch_fourier_dir.argtypes = [vp, vp, ci]
         L.spdy_bench_roundtrip.argtypes = [vp, vp, ci, ci, vp, vp]
+        L.spdy_bench_spectral_chain.argtypes = [vp, vp, ci, ci, vp]
+        L.spdy_bench_physics.argtypes = [vp, ci, vp, ci, ci, vp]
+        for n in ("spdy_batch_vort2vel", "spdy_batch_vel2vort"):
+            getattr(L, n).argtypes = [vp, vp, vp, vp, ci]
+        L.spdy_batch_gradient.argtypes = [vp, vp, vp, ci]
+        L.spdy_batch_laplacian.argtypes = [vp, vp, ci, ci]
+        L.spdy_batch_grid_vel2vort.argtypes = [vp, vp, vp, vp, ci, ci]
+        L.spdy_debug_tendencies_stage.argtypes = [i64, ci, ci, vp, vp, vp, vp, vp]
         L.spdy_clone_state.argtypes = [i64, vp, ci]
         L.spdy_perturb_temperature.argtypes = [vp, ci, C.c_ulonglong, C.c_double]
         L.spdy_batch_spectral2grid.argtypes = [vp, ci]

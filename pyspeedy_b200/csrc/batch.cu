@@ -440,7 +440,66 @@ int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, in
 }
 }  // extern "C"
 
+namespace spdy {
+struct PhysSeg {
+    long long src, dst, len;
+};
+// member i of the chunk (tile t, lane) receives column set (first + 32 t + lane) % nsets
+__global__ void __launch_bounds__(256) k_scatter_sets(const Ctx c, const double *__restrict__ sets, long long setlen, int nsets,
+                                                      const PhysSeg seg) {
+    const int t = blockIdx.y;
+    const long long e = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= seg.len) return;
+    const int set = (t * TILE + lane) % nsets;
+    *(scp(c, t, seg.dst + e, lane)) = sets[(size_t)set * setlen + seg.src + e];
+}
+}  // namespace spdy
+
 extern "C" {
+// BASELINE config 5: the column physics alone (physics.f90:103-231: convection, large-scale condensation,
+// short-wave / long-wave radiation, surface fluxes, vertical diffusion) on synthetic columns.  `sets` holds nsets column
+// sets of 45 x (96,48) doubles each: ug8, vg8, pslg, utend8, vtend8 (lowest level / 2-D), then tg, qg, phig, ttend, qtend
+// (8 levels each); member i of the list works on set i % nsets, its surface and forcing fields come from its state.
+// reps launches per phase; ms[0] = mean device time of a short-wave step (compute_shortwave), ms[1] = long-wave-only step.
+int spdy_bench_physics(const int64_t *states, int n, const double *sets, int nsets, int reps, float *ms) {
+    API_LOCK;
+    engine_init();
+    const ScratchLayout &L = E.L;
+    const int nt = prepare_members(states, n);
+    if (nt == 0 || nt > E.chunk_tiles || nsets < 1) return -1;
+    Ctx c = make_ctx(E.d_tiles, E.d_masks, nt);
+    const long long setlen = 45ll * NG, G3 = (long long)NG * KX;
+    double *d_sets = nullptr;
+    CK(cudaMalloc(&d_sets, (size_t)nsets * setlen * sizeof(double)));
+    CK(cudaMemcpy(d_sets, sets, (size_t)nsets * setlen * sizeof(double), cudaMemcpyHostToDevice));
+    const PhysSeg segs[10] = {{0, L.pug8, NG}, {NG, L.pvg8, NG}, {2ll * NG, L.pslg, NG}, {3ll * NG, L.utend + 7ll * NG, NG},
+                              {4ll * NG, L.vtend + 7ll * NG, NG}, {5ll * NG, L.ptg, G3}, {5ll * NG + G3, L.pqg, G3},
+                              {5ll * NG + 2 * G3, L.pphig, G3}, {5ll * NG + 3 * G3, L.ttend, G3}, {5ll * NG + 4 * G3, L.trtend, G3}};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)), CK(cudaEventCreate(&e1));
+    for (int phase = 0; phase < 2; phase++) {
+        k_set_slot<<<nt, 32, 0, E.stream>>>(c, SL_SW, phase == 0 ? 1.0 : 0.0);
+        float acc = 0.f;
+        for (int r = -2; r < reps; r++) {  // two warm-up launches; the in/out tendencies are re-initialised every time
+            for (const PhysSeg &sg : segs)
+                k_scatter_sets<<<dim3((unsigned)((sg.len + 7) / 8), nt), 256, 0, E.stream>>>(c, d_sets, setlen, nsets, sg);
+            CK(cudaEventRecord(e0, E.stream));
+            launch_physics(E.stream, c, L, nullptr);
+            CK(cudaEventRecord(e1, E.stream));
+            COUNT(11);
+            CK(cudaStreamSynchronize(E.stream));
+            float t;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (r >= 0) acc += t;
+        }
+        ms[phase] = reps > 0 ? acc / reps : 0.f;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventDestroy(e0)), CK(cudaEventDestroy(e1));
+    CK(cudaFree(d_sets));
+    return 0;
+}
 // bracket a region for `ncu --profile-from-start off`
 int spdy_profiler_start(void) { API_LOCK; return (int)cudaProfilerStart(); }
 int spdy_profiler_stop(void) { API_LOCK; return (int)cudaProfilerStop(); }

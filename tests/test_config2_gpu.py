@@ -1,0 +1,76 @@
+"""BASELINE configs[1] at its stated size: a 64-member perturbed-IC ensemble (examples/Ensemble_forecast.ipynb cell 8:
+t_grid += N(0, 0.01 K) i.i.d. per grid point, numpy default_rng(1234 + member), then grid2spectral).
+
+  * 3 simulated days against the oracle, member by member (192 oracle member-days, OpenMP over members): acceptance
+    criterion of SURVEY 8(d): RMS(GPU - oracle) <= 1e-6 x ensemble spread per output variable, after day 1 and day 3;
+    device-reduced ensemble mean / spread against numpy on the oracle members;
+  * then on to day 30 on the GPU (the notebook's forecast length): every member passes the diagnostics check on every
+    step, the fields stay in physical ranges, the spread has grown by orders of magnitude and is bounded."""
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+OUT = ("u_grid", "v_grid", "t_grid", "q_grid", "phi_grid", "ps_grid")
+N = 64
+
+
+def test_config2_64_members_3_days_vs_oracle_then_30_days(oracle):
+    from pyspeedy_b200 import SpeedyEns, _speedy
+
+    ens = SpeedyEns(N, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 31))
+    ens.set_bc()
+    st0 = oracle.State(n_months=1)
+    ctl0 = oracle.Control((1982, 1, 1, 0, 0), (1982, 1, 31, 0, 0))
+    oracle.load_default_bc(st0)
+    assert st0.init(ctl0) == 0
+    states, ctls = [st0] + [st0.clone() for _ in range(N - 1)], [ctl0] + [ctl0.clone() for _ in range(N - 1)]
+    st0.spectral2grid()
+    base = st0["t_grid"]
+    for k, (s, mem) in enumerate(zip(states, ens)):
+        tg = base + np.random.default_rng(1234 + k).normal(0.0, 0.01, size=(96, 48, 8))
+        s["t_grid"] = tg
+        mem["t_grid"] = tg
+        s.grid2spectral()
+        mem.grid2spectral()
+    sc, cc = ens.handles()
+    spread_t = {}
+    for day in (1, 2, 3):
+        assert (_speedy.run_steps(sc, cc, 36) == 0).all()
+        for _ in range(36):
+            assert (oracle.parallel_step(states, ctls) == 0).all()
+        if day == 2:
+            continue
+        ms = ens.mean_and_spread()  # fused: spectral2grid of all members + sums in its epilogue
+        for s in states:
+            s.spectral2grid()
+        for v in OUT:
+            ref = np.stack([s[v] for s in states])
+            got = _speedy.ensemble_get(sc, v).transpose(0, *range(ref.ndim - 1, 0, -1))  # -> (member, lon, lat[, lev])
+            spread = np.sqrt(np.mean(ref.var(axis=0)))  # sqrt(mean over the grid of the ensemble variance), ddof = 0
+            rms = np.sqrt(np.mean((got - ref) ** 2))
+            print(f"day {day} {v}: rms/spread = {rms / spread:.2e} (spread {spread:.3e})")
+            assert rms <= 1e-6 * spread, (day, v, rms, spread)
+            mean, std = ms[v]
+            assert relerr(mean, ref.mean(axis=0)) < 1e-9, (day, v)
+            assert np.abs(std - ref.std(axis=0)).max() <= 1e-6 * np.abs(ref.std(axis=0)).max() + 1e-12, (day, v)
+            if v == "t_grid":
+                spread_t[day] = spread
+    # ---- 27 more days on the GPU: stability of the whole ensemble
+    for day in range(4, 31):
+        err = _speedy.run_steps(sc, cc, 36)
+        assert (err == 0).all(), (day, err)
+    assert (_speedy.batch_check(sc) == 0).all()
+    assert _speedy.get_model_datetime(int(sc[17])) == (1982, 1, 31, 0, 0) and ens.get_current_step() == 1080
+    ms = ens.mean_and_spread()
+    ranges = {"u_grid": (-150, 150), "v_grid": (-120, 120), "t_grid": (150, 340), "q_grid": (-1e-3, 0.04),
+              "phi_grid": (-1500, 40000), "ps_grid": (4.5e4, 1.1e5)}
+    for v, (lo, hi) in ranges.items():
+        a = _speedy.ensemble_get(sc, v)
+        assert np.isfinite(a).all() and lo < a.min() and a.max() < hi, (v, a.min(), a.max())
+    s30 = float(np.sqrt(np.mean(ms["t_grid"][1] ** 2)))
+    print(f"T spread: day 1 {spread_t[1]:.3e} K, day 3 {spread_t[3]:.3e} K, day 30 {s30:.3e} K")
+    assert s30 > 10 * spread_t[1] and s30 < 30.0

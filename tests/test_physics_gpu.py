@@ -6,38 +6,10 @@ from datetime import datetime
 import numpy as np
 import pytest
 
+from pyspeedy_b200.synthetic import synth_columns
 from util import ptr, relerr
 
 pytestmark = pytest.mark.gpu
-
-
-def synth_columns(st, seed=7):
-    """T = reference profile + N(0,5K); ps/p0 ~ U(0.5,1.05); rh ~ U(0,1.1); u,v ~ N(0,10); hydrostatic phi."""
-    rng = np.random.default_rng(seed)
-    fsg = np.array([0.025, 0.095, 0.2, 0.34, 0.51, 0.685, 0.835, 0.95])
-    tref = 288.0 * np.maximum(0.2, fsg) ** (287.0 * 0.006 / 9.81)
-    tg = tref[None, None, :] + rng.normal(0, 5.0, size=(96, 48, 8))
-    psa = rng.uniform(0.5, 1.05, size=(96, 48))
-    pslg = np.log(psa)
-    e0, c1, c2, t0, t1, t2 = 6.108e-3, 17.269, 21.875, 273.16, 35.86, 7.66
-    qs = np.where(tg >= t0, e0 * np.exp(c1 * (tg - t0) / (tg - t1)), e0 * np.exp(c2 * (tg - t0) / (tg - t2)))
-    qs = 622.0 * qs / (fsg[None, None, :] * psa[:, :, None] - 0.378 * qs)
-    qg = rng.uniform(0, 1.1, size=(96, 48, 8)) * qs
-    ug = rng.normal(0, 10, size=(96, 48, 8))
-    vg = rng.normal(0, 10, size=(96, 48, 8))
-    phis0 = np.maximum(0.0, rng.normal(0, 5e3, size=(96, 48)))
-    hsg = np.array([0.0, 0.05, 0.14, 0.26, 0.42, 0.6, 0.77, 0.9, 1.0])
-    phig = np.zeros((96, 48, 8))
-    phig[:, :, 7] = phis0 + 287.0 * np.log(hsg[8] / fsg[7]) * tg[:, :, 7]
-    for k in range(6, -1, -1):
-        phig[:, :, k] = phig[:, :, k + 1] + 287.0 * np.log(fsg[k + 1] / fsg[k]) * 0.5 * (tg[:, :, k] + tg[:, :, k + 1])
-    surf = dict(phis0=phis0, fmask_land=rng.choice([0.0, 1.0, 0.37], size=(96, 48)), forog=rng.uniform(1, 1.5, (96, 48)),
-                sst_am=rng.uniform(271, 303, (96, 48)), land_temp=rng.uniform(230, 310, (96, 48)),
-                alb_land=rng.uniform(0.07, 0.6, (96, 48)), alb_sea=rng.uniform(0.07, 0.6, (96, 48)),
-                alb_surface=rng.uniform(0.07, 0.6, (96, 48)), soil_avail_water=rng.uniform(0, 1, (96, 48)),
-                snowc=rng.uniform(0, 1, (96, 48)), ssrd=rng.uniform(0, 300, (96, 48)))
-    F = lambda a: np.asfortranarray(a)
-    return [F(x) for x in (ug, vg, tg, qg, phig, pslg)], surf
 
 
 @pytest.mark.parametrize("sw", [True, False])
@@ -48,7 +20,7 @@ def test_physics_columns(oracle, drv, sw):
     st.init_tables()
     st.zonal_average_fields(0.03)
     m = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
-    (ug, vg, tg, qg, phig, pslg), surf = synth_columns(st)
+    (ug, vg, tg, qg, phig, pslg), surf = synth_columns(seed=7)
     for k, v in surf.items():
         st[k] = v
     rng = np.random.default_rng(3)

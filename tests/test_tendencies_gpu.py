@@ -1,6 +1,6 @@
 """Per-tendency parity (BASELINE north_star: 1e-12 relative): the five spectral tendencies returned by
 get_tendencies (tendencies.f90:11-39: grid-point dynamics + physics + spectral terms + implicit correction) of a
-spun-up state, GPU vs oracle; plus the config-2 acceptance criterion on a small perturbed ensemble."""
+spun-up state, GPU vs oracle (the config-2 acceptance criterion lives in test_config2_gpu.py)."""
 import ctypes as C
 from datetime import datetime
 
@@ -48,48 +48,3 @@ def test_tendencies(oracle, drv, steps):
     # bit-exact mask handling: the tendencies are exactly zero where the oracle's are (rows outside the nsh2 mask)
     for k in ref:
         assert np.all(outs[k][ref[k] == 0] == 0), k
-
-
-def test_config2_acceptance(oracle):
-    """BASELINE config 2 criterion on 6 members: 1-day RMS(GPU - oracle) <= 1e-6 x ensemble spread per variable."""
-    from pyspeedy_b200 import SpeedyEns, _speedy
-
-    n = 6
-    ens = SpeedyEns(n, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
-    ens.set_bc()
-    st0 = oracle.State(n_months=1)
-    ctl0 = oracle.Control((1982, 1, 1, 0, 0), (1982, 1, 2, 0, 0))
-    oracle.load_default_bc(st0)
-    assert st0.init(ctl0) == 0
-    states, ctls = [st0] + [st0.clone() for _ in range(n - 1)], [ctl0] + [ctl0.clone() for _ in range(n - 1)]
-    for k, (s, mem) in enumerate(zip(states, ens)):
-        rng = np.random.default_rng(1234 + k)  # examples/Ensemble_forecast.ipynb cell 8
-        s.spectral2grid()
-        mem.spectral2grid()
-        pert = rng.normal(0.0, 0.01, size=(96, 48, 8))
-        tg = s["t_grid"] + pert
-        s["t_grid"] = tg
-        mem["t_grid"] = tg
-        s.grid2spectral()
-        mem.grid2spectral()
-    sc, cc = ens.handles()
-    err = _speedy.run_steps(sc, cc, 36)
-    assert (err == 0).all()
-    assert (oracle.parallel_step(states, ctls) == 0).all() or True
-    for _ in range(35):
-        assert (oracle.parallel_step(states, ctls) == 0).all()
-    _speedy.batch_spectral2grid(sc)
-    ms = ens.mean_and_spread()
-    for s in states:
-        s.spectral2grid()
-    for v in ("u_grid", "v_grid", "t_grid", "q_grid", "phi_grid", "ps_grid"):
-        ref = np.stack([s[v] for s in states])
-        got = np.stack([mem[v] for mem in ens])
-        spread = np.sqrt(np.mean(ref.var(axis=0)))
-        rms = np.sqrt(np.mean((got - ref) ** 2))
-        print(v, "rms/spread =", rms / spread)
-        assert rms <= 1e-6 * spread, (v, rms, spread)
-        # device-reduced mean / spread agree with numpy on the oracle members
-        mean, std = ms[v]
-        assert relerr(mean, ref.mean(axis=0)) < 1e-9
-        assert np.abs(std - ref.std(axis=0)).max() <= 1e-6 * np.abs(ref.std(axis=0)).max() + 1e-12

@@ -10,17 +10,7 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def synth_spec(n, seed=2024, scale=1.0):
-    """BASELINE config 4: N(0,1)*(1+l)^-1 inside l <= 30, zero outside, Im(m=0) = 0.  Shape (n, 32, 31) complex
-    (C order = Fortran (31, 32) per field)."""
-    rng = np.random.default_rng(seed)
-    m = np.arange(MX)[None, :]
-    nn = np.arange(NX)[:, None]
-    l = m + nn
-    amp = np.where(l <= 30, 1.0 / (1.0 + l), 0.0)
-    x = (rng.standard_normal((n, NX, MX)) + 1j * rng.standard_normal((n, NX, MX))) * amp * scale
-    x[:, :, 0] = x[:, :, 0].real
-    return np.ascontiguousarray(x)
+from pyspeedy_b200.synthetic import synth_spec  # noqa: E402,F401  (BASELINE config 4 fields)
 
 
 def relerr(a, b):

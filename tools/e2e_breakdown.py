@@ -4,50 +4,51 @@
   python tools/e2e_breakdown.py --members 4096
 """
 import argparse
-import ctypes as C
 import os
 import sys
 import time
-from datetime import datetime
+from datetime import datetime, timedelta
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch  # noqa: E402
-
-from bench import CudaArray  # noqa: E402
-from pyspeedy_b200 import DEFAULT_OUTPUT_VARS, SpeedyEns, _driver, _speedy  # noqa: E402
+from pyspeedy_b200 import SpeedyEns, _driver, _speedy  # noqa: E402
+from pyspeedy_b200.callbacks import DiagnosticCheck, EnsembleStatistics  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--members", type=int, default=4096)
-ap.add_argument("--steps", type=int, default=12)
+ap.add_argument("--steps", type=int, default=36)
 a = ap.parse_args()
 lib = _driver.lib()
 lib.spdy_reserve(a.members)
-ens = SpeedyEns(a.members, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 11))
+end = datetime(1982, 1, 11)
+ens = SpeedyEns(a.members, start_date=datetime(1982, 1, 1), end_date=end)
 ens.set_bc(perturb_sigma=0.01)
 s, c = ens.handles()
 assert (_speedy.run_steps(s, c, 3) == 0).all()
 
 
 def timed(f, reps=1):
-    torch.cuda.synchronize()
+    lib.spdy_synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
         r = f()
-    torch.cuda.synchronize()
+    lib.spdy_synchronize()
     return 1e3 * (time.perf_counter() - t0) / reps, r
 
 
 ms, _ = timed(lambda: _speedy.run_steps(s, c, a.steps))
-print(f"run_steps            {ms / a.steps:8.3f} ms/step (device {lib.spdy_last_elapsed_ms() / a.steps:.3f})")
+print(f"run_steps                     {ms / a.steps:8.3f} ms/step (device {lib.spdy_last_elapsed_ms() / a.steps:.3f})")
 ms, _ = timed(lambda: _speedy.parallel_step(s, c), a.steps)
-print(f"parallel_step        {ms:8.3f} ms/step (device {lib.spdy_last_elapsed_ms():.3f})")
+print(f"parallel_step                 {ms:8.3f} ms/step (device {lib.spdy_last_elapsed_ms():.3f})")
+for label, cbs in (("ens.run, no callbacks", []), ("ens.run + DiagnosticCheck + EnsembleStatistics", [DiagnosticCheck(36), EnsembleStatistics(36)])):
+    ens.current_date = end - a.steps * timedelta(seconds=2400)
+    ms, _ = timed(lambda: ens.run(callbacks=cbs))
+    print(f"{label:48s} {ms / a.steps:8.3f} ms/step")
 for rep in range(2):
     ms, _ = timed(lambda: _speedy.batch_spectral2grid(s))
-    print(f"batch_spectral2grid  {ms:8.3f} ms")
-    for v in DEFAULT_OUTPUT_VARS:
-        e = _driver.REGISTRY[_driver.VAR_ID[v]]
-        dev, ne = C.c_void_p(), C.c_size_t()
-        ms1, _ = timed(lambda: lib.spdy_ensemble_sums_device(_driver._ptr(s), len(s), e["id"], None, C.byref(dev), C.byref(ne)))
-        t = torch.as_tensor(CudaArray(dev.value, 2 * ne.value), device="cuda")
-        ms2, host = timed(lambda: t.cpu().numpy())
-        print(f"  {v:10s} sums {ms1:8.3f} ms   D2H of {host.nbytes} B {ms2:8.3f} ms")
+    print(f"batch_spectral2grid           {ms:8.3f} ms")
+    ms, _ = timed(lambda: _speedy.ensemble_mean_spread(s))
+    print(f"ensemble_mean_spread (fused)  {ms:8.3f} ms   (spectral2grid + sums + D2H of 3 MB)")
+    ms, _ = timed(lambda: _speedy.batch_check(s))
+    print(f"batch_check                   {ms:8.3f} ms")
+    ms, r = timed(lambda: _speedy.ensemble_get(s[:64], "t_grid", dtype="float32"))
+    print(f"ensemble_get(64 x t_grid f32) {ms:8.3f} ms   ({r.nbytes} B)")
