@@ -112,7 +112,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Number of samples so far: the samples between two marks were taken during the region in between."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -120,7 +124,8 @@ class ClockSampler:
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[first:(last + 1 if last is not None else None)] or self.rows[-1:]
+        for r in rows:
             try:
                 sm.append(float(r[0])), mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -227,22 +232,26 @@ def run_config3(args):
     s, c = ens.handles()
 
     # ---- warm-up, then the device-resident timed region --------------------------------------------------------
+    # the clock sampler (nvidia-smi -lms 100 needs a few hundred ms to deliver its first line) starts before the warm-up;
+    # the samples taken between the two marks below are those of the timed region
+    sampler = ClockSampler(comm.local_rank)
+    if rank == 0:
+        sampler.start()
     warm = max(args.warmup, 3)
     err = _speedy.run_steps(s, c, warm)
     assert (err == 0).all(), err
-    sampler = ClockSampler(comm.local_rank)
     comm.barrier()
     l0 = lib.spdy_kernel_launches()
-    if rank == 0:
-        sampler.start()
+    mark0 = sampler.mark()
     lib.spdy_profiler_start()  # cudaProfilerStart/Stop: `ncu --profile-from-start off` lists exactly the timed launches
     t0 = time.perf_counter()
     err = _speedy.run_steps(s, c, args.steps)  # returns after the stream has drained (device events bracket the steps)
     t_local = time.perf_counter() - t0
     lib.spdy_profiler_stop()
     dev_ms = float(lib.spdy_last_elapsed_ms())
+    mark1 = sampler.mark()
     comm.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, mark1) if rank == 0 else None
     launches = lib.spdy_kernel_launches() - l0
     assert (err == 0).all(), err
     t_max, dev_ms_max = comm.max(t_local), comm.max(dev_ms)

@@ -58,6 +58,9 @@ int spdy_synchronize(void);
 /* elapsed device time (ms) of the last spdy_run_steps / spdy_parallel_step call, CUDA events on the launch stream */
 float spdy_last_elapsed_ms(void);
 long long spdy_kernel_launches(void);       /* kernels launched by this library so far */
+/* host wall time (us) of the phases of the last step / parallel_step / run_steps call: prologue (entry to first launch),
+ * kernel launches, waiting for the GPU, epilogue */
+void spdy_last_call_host_us(double *out4);
 /* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` sees only a bracketed region */
 int spdy_profiler_start(void);
 int spdy_profiler_stop(void);

@@ -56,16 +56,22 @@ class ModelCheckpoint(BaseCallback):
         self.output_dir = output_dir
         self.history_interval = interval
         super().__init__(verbose=verbose, interval=interval, spinup_date=spinup_date)
-        self.dataframe = None
+        self._frames, self._merged = [], None
+
+    @property
+    def dataframe(self):
+        """The time series so far.  The reference re-merges the whole series at every checkpoint (xr.merge of the
+        growing dataset, O(n^2) copies); here the checkpoints are kept as they come and merged once, when read."""
+        if self._merged is None and self._frames:
+            self._merged = self._frames[0] if len(self._frames) == 1 else Dataset.merge(self._frames)
+            self._frames = [self._merged]
+        return self._merged
 
     def __call__(self, model_instance):
         if self.skip_flag(model_instance):
             return
-        model_df = model_instance.to_dataframe(variables=self.variables)
-        if self.dataframe is None:
-            self.dataframe = model_df
-        else:
-            self.dataframe = Dataset.merge((self.dataframe, model_df))
+        self._frames.append(model_instance.to_dataframe(variables=self.variables))
+        self._merged = None
 
 
 class EnsembleStatistics(BaseCallback):

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <map>
@@ -732,8 +733,18 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
 }
 
 // bind controls, run nsteps for the listed members; returns per-member first error
+// host-side wall time of the phases of the last step_members call (us): prologue (entry -> first launch), launch loop,
+// wait for the GPU, epilogue; read with spdy_last_call_host_us (tools/e2e_breakdown.py)
+static double g_host_us[4] = {0, 0, 0, 0};
+static inline double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {
     engine_init();
+    const double t_entry = now_us();
+    double t_wait = 0.0, t_launch = 0.0;
     int failed = 0;
     std::vector<int64_t> run;
     std::vector<int> idx;
@@ -779,12 +790,15 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     CK(cudaMemsetAsync(E.d_err, 0, (size_t)nt * TILE * sizeof(int), E.stream));  // sticky within this call (k_collect_err)
     bool any_failed = false;
     CK(cudaEventRecord(E.ev0, E.stream));
+    const double t_first = now_us();
     for (int s = 0; s < nsteps; s++) {
+        const double t_s0 = now_us();
         bool any_daily = false;
         for (size_t q = 0; q < run.size(); q++) any_daily |= (member_of(run[q])->current_step % NSTEPS == 0);
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
             run_chunk_step(t0, std::min(E.chunk_tiles, nt - t0), any_daily);
         }
+        t_launch += now_us() - t_s0;
         for (size_t q = 0; q < run.size(); q++) member_of(run[q])->current_step += 1;
         const bool last = (s == nsteps - 1);
         const bool readback = per_step_sync || last || ((s + 1) % NSTEPS == 0);
@@ -801,7 +815,9 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
             // error codes: read back at most once a day in batched mode; the device keeps the first non-zero code of
             // every member and freezes a failed member for the rest of the call (k_collect_err)
             CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+            const double t_w0 = now_us();
             CK(cudaStreamSynchronize(E.stream));
+            t_wait += now_us() - t_w0;
             for (size_t q = 0; q < run.size(); q++) {
                 const int code = E.h_err[epos[q]];
                 if (code != 0 && err_out[idx[q]] == 0) {
@@ -836,6 +852,9 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
                 }
     }
     for (int i = 0; i < n; i++) failed += (err_out[i] != 0 && err_out[i] != -1) ? 1 : 0;
+    const double t_end = now_us();
+    g_host_us[0] = t_first - t_entry, g_host_us[1] = t_launch, g_host_us[2] = t_wait;
+    g_host_us[3] = (t_end - t_first) - t_launch - t_wait;
     return failed;
 }
 
@@ -1022,6 +1041,10 @@ int spdy_synchronize(void) {
     API_LOCK;
     if (E.ready) CK(cudaStreamSynchronize(E.stream));
     return 0;
+}
+void spdy_last_call_host_us(double *out4) {
+    API_LOCK;
+    for (int i = 0; i < 4; i++) out4[i] = g_host_us[i];
 }
 float spdy_last_elapsed_ms(void) { API_LOCK; return E.last_ms; }
 long long spdy_kernel_launches(void) { API_LOCK; return g_launches; }

@@ -68,6 +68,7 @@ class Dataset:
                             vals.append(v)
                 out_coords[dim] = sorted(vals)
         dv = {}
+        pos = {d: {v: i for i, v in enumerate(out_coords[d])} for d in ("time", "ens") if d in out_coords}
         for name, (dims, a0) in first.data_vars.items():
             shape = [len(out_coords[d]) if d in ("time", "ens") else a0.shape[i] for i, d in enumerate(dims)]
             out = np.full(shape, np.nan, dtype=a0.dtype)
@@ -75,18 +76,10 @@ class Dataset:
                 if name not in ds.data_vars:
                     continue
                 _, a = ds.data_vars[name]
-                idx = [slice(None)] * len(dims)
-                sub = [None] * len(dims)
-                for i, d in enumerate(dims):
-                    if d in ("time", "ens"):
-                        sub[i] = [out_coords[d].index(v) for v in ds.coords[d]]
-                it = np.ndindex(*[len(s) if s is not None else 1 for s in sub])
-                for pos in it:
-                    src, dst = list(idx), list(idx)
-                    for i, s in enumerate(sub):
-                        if s is not None:
-                            src[i], dst[i] = pos[i], s[pos[i]]
-                    out[tuple(dst)] = a[tuple(src)]
+                # one vectorised assignment per dataset: open-mesh index over the merged dims, full ranges elsewhere
+                ix = [np.array([pos[d][v] for v in ds.coords[d]]) if d in pos else np.arange(a.shape[i])
+                      for i, d in enumerate(dims)]
+                out[np.ix_(*ix)] = a
             dv[name] = (dims, out)
         return Dataset(dv, out_coords, first.attrs)
 

@@ -27,8 +27,8 @@ def test_config2_64_members_3_days_vs_oracle_then_30_days(oracle):
     ctl0 = oracle.Control((1982, 1, 1, 0, 0), (1982, 1, 31, 0, 0))
     oracle.load_default_bc(st0)
     assert st0.init(ctl0) == 0
+    st0.spectral2grid()  # before cloning: grid2spectral below converts ALL *_grid variables of a member
     states, ctls = [st0] + [st0.clone() for _ in range(N - 1)], [ctl0] + [ctl0.clone() for _ in range(N - 1)]
-    st0.spectral2grid()
     base = st0["t_grid"]
     for k, (s, mem) in enumerate(zip(states, ens)):
         tg = base + np.random.default_rng(1234 + k).normal(0.0, 0.01, size=(96, 48, 8))

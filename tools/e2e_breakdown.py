@@ -39,6 +39,11 @@ ms, _ = timed(lambda: _speedy.run_steps(s, c, a.steps))
 print(f"run_steps                     {ms / a.steps:8.3f} ms/step (device {lib.spdy_last_elapsed_ms() / a.steps:.3f})")
 ms, _ = timed(lambda: _speedy.parallel_step(s, c), a.steps)
 print(f"parallel_step                 {ms:8.3f} ms/step (device {lib.spdy_last_elapsed_ms():.3f})")
+import numpy as np  # noqa: E402
+
+us = np.zeros(4)
+lib.spdy_last_call_host_us(_driver._ptr(us))
+print("  host phases of the last parallel_step call (us): prologue %.0f, launches %.0f, wait %.0f, epilogue %.0f" % tuple(us))
 for label, cbs in (("ens.run, no callbacks", []), ("ens.run + DiagnosticCheck + EnsembleStatistics", [DiagnosticCheck(36), EnsembleStatistics(36)])):
     ens.current_date = end - a.steps * timedelta(seconds=2400)
     ms, _ = timed(lambda: ens.run(callbacks=cbs))
