@@ -19,6 +19,7 @@ process id and master port.
     ens.run(callbacks=[EnsembleStatistics()])       # mean / spread over all 4096 members on every rank
 """
 import os
+import sys
 import tempfile
 import time
 
@@ -147,7 +148,18 @@ def init(rank=None, world=None, local_rank=None):
             return buf.raw
 
         blob = exchange(rank, world, make, 128)
-        rc = lib.spdy_comm_init(rank, world, C.create_string_buffer(blob, 128))
+        # NCCL announces itself ("NCCL version ...") on STDOUT when the first communicator comes up; programs whose
+        # stdout is a protocol (bench.py prints one JSON line) must not see that: route fd 1 to stderr meanwhile
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = lib.spdy_comm_init(rank, world, C.create_string_buffer(blob, 128))
+            if rc == 0:
+                lib.spdy_comm_barrier()  # first collective: connection set-up happens here, not inside a timed region
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         if rc != 0:
             raise RuntimeError(f"spdy_comm_init failed: {rc}")
     return Comm(rank, world, local_rank)
