@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(32) k_diag_partial(const Ctx c, const int time
 // mode 0: check only (initialisation).  mode 1: step counter + 1 before the check, calendar advance after it for
 // the members that passed (model_control.f90:113-163).
 __device__ __forceinline__ void advance_calendar(const Ctx &c, int t, int lane);
-__global__ void __launch_bounds__(256) k_diag_final(const Ctx c, const int time_lev, const long long part, const int mode) {
+// err_out / masks (mode 1): sticky error codes of the driver call and the call's active-lane masks -- a member that fails is
+// taken out of the rest of a multi-step call (see step_members in engine.cu)
+__global__ void __launch_bounds__(256) k_diag_final(const Ctx c, const int time_lev, const long long part, const int mode,
+                                                    int *__restrict__ err_out, unsigned *__restrict__ masks) {
     __shared__ int s_bad[KX][TILE];
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5, t = blockIdx.x;
     const size_t lev = (size_t)NSP * TILE, tl = (size_t)KX * lev * (time_lev - 1);
@@ -431,7 +434,12 @@ __global__ void __launch_bounds__(256) k_diag_final(const Ctx c, const int time_
     for (int kk = 0; kk < KX; kk++) bad |= s_bad[kk][lane];
     if (mode == 1) slot(c, t, lane, SL_STEP) = slot(c, t, lane, SL_STEP) + 1.0;
     if (bad) slot(c, t, lane, SL_ERR) = -2.0;
-    if (mode == 1 && !bad && slot(c, t, lane, SL_ERR) == 0.0) advance_calendar(c, t, lane);
+    const int code = (int)slot(c, t, lane, SL_ERR);
+    if (mode == 1 && code == 0) advance_calendar(c, t, lane);
+    if (err_out && code != 0 && err_out[t * TILE + lane] == 0) {
+        err_out[t * TILE + lane] = code;
+        atomicAnd(&masks[t], ~(1u << lane));
+    }
 }
 
 // --------------------------------------------------------------------------------------------- member control
@@ -439,8 +447,7 @@ __global__ void __launch_bounds__(256) k_diag_final(const Ctx c, const int time_
 __device__ __forceinline__ double date_code(const Ctx &c, int t, int lane) {
     return (slot(c, t, lane, SL_YEAR) * 16.0 + slot(c, t, lane, SL_MONTH)) * 32.0 + slot(c, t, lane, SL_DAY);
 }
-__global__ void k_control_pre(const Ctx c) {
-    const int lane = threadIdx.x, t = blockIdx.x;
+__device__ __forceinline__ void control_pre_lane(const Ctx &c, const int t, const int lane) {
     if (!lane_active(c, t, lane)) return;
     const int step = (int)slot(c, t, lane, SL_STEP);
     // coupler climatology cache: valid for the current date unless the host touched the member since the last step
@@ -449,6 +456,31 @@ __global__ void k_control_pre(const Ctx c) {
     slot(c, t, lane, SL_ERR) = 0.0;
     slot(c, t, lane, SL_DAILY) = (step % NSTEPS == 0) ? 1.0 : 0.0;
     slot(c, t, lane, SL_SW) = (step % NSTRAD == 0) ? 1.0 : 0.0;
+}
+__global__ void k_control_pre(const Ctx c) { control_pre_lane(c, blockIdx.x, threadIdx.x); }
+
+// The spectral pre-operators of a step in ONE launch, warp per coefficient (m,n): set_geopotential of time level 1
+// (geopotential.f90:36-77), vort2vel of time level j2 for the dynamics and of the lowest level of time level 1 for the
+// physics (spectral.f90:190-214), grad(ps) (spectral.f90:275-296); with_control: the first warp of a tile also sets the
+// member flags of the step (speedy.f90:41-53; on daily steps a separate launch does it before the forcing kernels).
+// tri: only the rows n <= 31 - m that the fused inverse transform reads.
+__global__ void __launch_bounds__(128) k_preops(const Ctx c, const ScratchLayout L, const int j2, const int tri,
+                                                const int with_control) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (with_control && q == 0) control_pre_lane(c, t, lane);
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE, lev = (size_t)NSP * TILE;
+    geopotential_elem(stp(c, t, c.off[V_t], lane) + e, stp(c, t, c.off[V_phis], lane) + e, stp(c, t, c.off[V_phi], lane) + e, m,
+                      lane_active(c, t, lane));
+    if (tri && m + n > NTRUNC + 1) return;
+    const size_t tl2 = (size_t)(j2 - 1) * KX * lev;
+    const double *pv = stp(c, t, c.off[V_vor], lane), *pd = stp(c, t, c.off[V_div], lane);
+    double *pu = scp(c, t, L.ucos, lane), *pw = scp(c, t, L.vcos, lane);
+#pragma unroll 2
+    for (int k = 0; k < KX; k++) uvspec_elem(c.G, pv + tl2 + k * lev, pd + tl2 + k * lev, pu + k * lev, pw + k * lev, m, n);
+    uvspec_elem(c.G, pv + 7 * lev, pd + 7 * lev, scp(c, t, L.ucosp8, lane), scp(c, t, L.vcosp8, lane), m, n);
+    gradient_elem(c.G, stp(c, t, c.off[V_ps], lane) + (size_t)(j2 - 1) * lev, scp(c, t, L.dpx, lane), scp(c, t, L.dpy, lane), m, n);
 }
 
 __device__ __forceinline__ int days_in_month(int mth) {
@@ -524,9 +556,13 @@ void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int 
     if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
     else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
 }
-void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part, int mode) {
+void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part, int mode, int *err_out = nullptr,
+                 unsigned *masks = nullptr) {
     k_diag_partial<<<dim3(KX * (MX - 1), c.ntiles), 32, 0, s>>>(c, time_lev, part);
-    k_diag_final<<<c.ntiles, 256, 0, s>>>(c, time_lev, part, mode);
+    k_diag_final<<<c.ntiles, 256, 0, s>>>(c, time_lev, part, mode, err_out, masks);
+}
+void launch_preops(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int j2, int tri, int with_control) {
+    k_preops<<<dim3(NSPC / 4, c.ntiles), 128, 0, s>>>(c, L, j2, tri, with_control);
 }
 void launch_control_pre(cudaStream_t s, const Ctx &c) { k_control_pre<<<c.ntiles, 32, 0, s>>>(c); }
 void launch_update_forcing_params(cudaStream_t s, const Ctx &c) { k_update_forcing_params<<<c.ntiles, 32, 0, s>>>(c); }

@@ -383,19 +383,6 @@ __global__ void k_scatter(double *arena, long long tile_elems, int tile, int lan
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) arena[((long long)tile * tile_elems + off + i) * TILE + lane] = src[i];
 }
-// Error codes of a driver call are STICKY: `out` (zeroed when the call starts) keeps the first non-zero code of every
-// member, and a member that fails is taken out of the call's active-lane mask, so that the remaining steps of a
-// multi-step call leave it exactly as the failing step left it (device calendar not advanced, speedy.f90:62-69) instead
-// of stepping a blown-up state that may turn into NaNs -- which pass check_diagnostics, every NaN comparison being false.
-__global__ void k_collect_err(const Ctx c, int *out, unsigned *masks) {  // out[tile_in_chunk*32 + lane]
-    const int lane = threadIdx.x, t = blockIdx.x;
-    if (!lane_active(c, t, lane)) return;
-    const int code = (int)slot(c, t, lane, SL_ERR);
-    if (code != 0 && out[t * TILE + lane] == 0) {
-        out[t * TILE + lane] = code;
-        atomicAnd(&masks[t], ~(1u << lane));
-    }
-}
 __global__ void k_spec_trunc(const Ctx c, FieldRef f, int nfields) {  // zero l > trunc (spectral.f90:309-314)
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     if (q >= NSPC) return;
@@ -586,17 +573,14 @@ static void run_forcing(const Ctx &c, int imode) {
 
 static int g_dump_stage = 2;  // tendency dump: 1 = before implicit_terms, 2 = as returned by get_tendencies
 // step(j1, j2, dt) of time_stepping.f90:38-147: tendencies + diffusion + time integration
-static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, int impl_idx, long long dump = -1) {
+static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, int impl_idx, long long dump = -1,
+                          int with_control = 0) {
     const ScratchLayout &L = E.L;
     const long long tl2 = (long long)(j2 - 1) * NSP * KX;
-    // spectral pre-operators: geopotential (time level 1), uvspec, grad(ps)
-    launch_geopotential(E.stream, c, E.off[V_t], E.off[V_phis], E.off[V_phi]);
-    // k_spec2grid_mma3 reads the rows inside the nsh2 mask only: the pre-operators skip the other 47 % of each field
-    const int tri = fused_transforms() ? 1 : 0;
-    launch_uvspec(E.stream, c, E.off[V_vor] + tl2, E.off[V_div] + tl2, REF_SCR | L.ucos, REF_SCR | L.vcos, KX, tri);
-    launch_uvspec(E.stream, c, E.off[V_vor] + 7ll * NSP, E.off[V_div] + 7ll * NSP, REF_SCR | L.ucosp8, REF_SCR | L.vcosp8, 1, tri);
-    launch_gradient(E.stream, c, E.off[V_ps] + (long long)(j2 - 1) * NSP, REF_SCR | L.dpx, REF_SCR | L.dpy, tri);
-    COUNT(4);
+    // spectral pre-operators in one launch: geopotential (time level 1), uvspec, grad(ps).  k_spec2grid_mma3 reads the rows
+    // inside the nsh2 mask only: uvspec and the gradient skip the other 47 % of each field
+    launch_preops(E.stream, c, L, j2, fused_transforms() ? 1 : 0, with_control);
+    COUNT(1);
     prof_mark(E.stream, PC_PREOPS);
     run_inverse(c, E.d_inv[j2 - 1], 77);
     if (fuse_dyn_physics()) {  // one kernel: the column's dynamical tendencies stay in registers (physics.cu)
@@ -618,14 +602,17 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
 }
 
 // do_single_step (speedy.f90:20-74) for one chunk of tiles
-static void run_model_step(const Ctx &c, bool any_daily) {
+static void run_model_step(const Ctx &c, bool any_daily, int *err_out, unsigned *masks) {
     prof_mark(E.stream, -1);
-    launch_control_pre(E.stream, c);
-    COUNT(1);
-    if (any_daily) run_forcing(c, 1);
+    if (any_daily) {  // the daily forcing kernels read the flags of the step: set them first
+        launch_control_pre(E.stream, c);
+        COUNT(1);
+        run_forcing(c, 1);
+    }
     prof_mark(E.stream, PC_FORCING);
-    run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2);
-    launch_diag(E.stream, c, 2, E.L.diagp, 1);  // step counter, check_diagnostics, calendar
+    run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2, -1, any_daily ? 0 : 1);
+    // step counter, check_diagnostics, calendar, sticky error codes of the call (k_diag_final)
+    launch_diag(E.stream, c, 2, E.L.diagp, 1, err_out, masks);
     launch_couple(E.stream, c, 0);
     prof_mark(E.stream, PC_POST);
     COUNT(3);
@@ -704,9 +691,7 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
     Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);
     const bool use_graph = ntc <= graph_max_tiles() && !P.on && g_eager_done[any_daily ? 1 : 0];
     if (!use_graph) {
-        run_model_step(c, any_daily);
-        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, E.d_masks + t0);
-        COUNT(1);
+        run_model_step(c, any_daily, E.d_err + t0 * TILE, E.d_masks + t0);
         g_eager_done[any_daily ? 1 : 0] = true;
         return;
     }
@@ -718,9 +703,7 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
         const long long l0 = g_launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(E.stream, cudaStreamCaptureModeThreadLocal));
-        run_model_step(c, any_daily);
-        k_collect_err<<<ntc, 32, 0, E.stream>>>(c, E.d_err + t0 * TILE, E.d_masks + t0);
-        COUNT(1);
+        run_model_step(c, any_daily, E.d_err + t0 * TILE, E.d_masks + t0);
         CK(cudaStreamEndCapture(E.stream, &graph));
         CK(cudaGraphInstantiate(&sg.exec, graph, 0));
         CK(cudaGraphDestroy(graph));
@@ -787,7 +770,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         int month_idx;
     };
     std::vector<SavedDate> saved(per_step_sync ? run.size() : 0);
-    CK(cudaMemsetAsync(E.d_err, 0, (size_t)nt * TILE * sizeof(int), E.stream));  // sticky within this call (k_collect_err)
+    CK(cudaMemsetAsync(E.d_err, 0, (size_t)nt * TILE * sizeof(int), E.stream));  // sticky within this call (k_diag_final)
     bool any_failed = false;
     CK(cudaEventRecord(E.ev0, E.stream));
     const double t_first = now_us();
@@ -813,7 +796,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         }
         if (readback) {
             // error codes: read back at most once a day in batched mode; the device keeps the first non-zero code of
-            // every member and freezes a failed member for the rest of the call (k_collect_err)
+            // every member and freezes a failed member for the rest of the call (k_diag_final)
             CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             const double t_w0 = now_us();
             CK(cudaStreamSynchronize(E.stream));

@@ -354,14 +354,9 @@ __global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, Field
 }
 
 // gradient (spectral.f90:275-296)
-__global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, FieldRef dx, FieldRef dy, int tri) {
-    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
-    if (q >= NSPC) return;
-    const int m = q % MX, n = q / MX;
-    if (tri && m + n > NTRUNC + 1) return;  // see k_uvspec
-    const GlobTables *G = c.G;
-    const double *p = refp(c, t, psi, lane);
-    double *px = refp(c, t, dx, lane), *py = refp(c, t, dy, lane);
+// gradient (spectral.f90:275-296) at coefficient (m,n)
+__device__ __forceinline__ void gradient_elem(const GlobTables *G, const double *p, double *px, double *py, int m, int n) {
+    const int q = m + MX * n;
     const size_t e = (size_t)(2 * m + M2 * n) * TILE, up = (size_t)M2 * TILE;
     const double gx = G->gradx[m];
     px[e] = -(gx * p[e + TILE]);
@@ -375,16 +370,18 @@ __global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, Fie
         py[e + TILE] = -G->gradym[q] * p[e - up + TILE] + G->gradyp[q] * p[e + up + TILE];
     }
 }
-
-// geopotential (geopotential.f90:36-77): phi from T(time level) and phis ; one warp per coefficient
-__global__ void __launch_bounds__(128) k_geopotential(const Ctx c, FieldRef tref_, FieldRef phis, FieldRef phi) {
+__global__ void __launch_bounds__(128) k_gradient(const Ctx c, FieldRef psi, FieldRef dx, FieldRef dy, int tri) {
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     if (q >= NSPC) return;
     const int m = q % MX, n = q / MX;
-    const size_t e = (size_t)(2 * m + M2 * n) * TILE, lev = (size_t)NSP * TILE;
-    const double *T = refp(c, t, tref_, lane) + e, *ps = refp(c, t, phis, lane) + e;
-    double *ph = refp(c, t, phi, lane) + e;
-    const bool act = lane_active(c, t, lane);
+    if (tri && m + n > NTRUNC + 1) return;  // see k_uvspec
+    gradient_elem(c.G, refp(c, t, psi, lane), refp(c, t, dx, lane), refp(c, t, dy, lane), m, n);
+}
+
+// geopotential (geopotential.f90:36-77): phi from T(time level) and phis ; one warp per coefficient
+// set_geopotential (geopotential.f90:36-77) at coefficient (m,n): hydrostatic integration + lapse-rate correction on m = 0
+__device__ __forceinline__ void geopotential_elem(const double *T, const double *ps, double *ph, const int m, const bool act) {
+    const size_t lev = (size_t)NSP * TILE;
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
         double tk[KX], p[KX];
@@ -402,6 +399,13 @@ __global__ void __launch_bounds__(128) k_geopotential(const Ctx c, FieldRef tref
             for (int k = 0; k < KX; k++) ph[k * lev + cc * TILE] = p[k];
         }
     }
+}
+__global__ void __launch_bounds__(128) k_geopotential(const Ctx c, FieldRef tref_, FieldRef phis, FieldRef phi) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    const size_t e = (size_t)(2 * m + M2 * n) * TILE;
+    geopotential_elem(refp(c, t, tref_, lane) + e, refp(c, t, phis, lane) + e, refp(c, t, phi, lane) + e, m, lane_active(c, t, lane));
 }
 
 // ------------------------------------------------------------------------------------------------- launchers
