@@ -427,6 +427,7 @@ int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, in
     // limit event usage: only the first chunk of the step is instrumented (events are reused per class otherwise)
     E.chunk_tiles = saved;
     step_members(hs, cs, n, 1, err, true);
+    CK(cudaStreamSynchronize(E.stream));  // the per-step call returns before the step's last kernel has finished
     P.on = false;
     int start = -1;
     for (int i = 0; i < P.n; i++) {

@@ -100,7 +100,8 @@ struct Engine {
     bool ready = false;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_err = nullptr;
+    bool last_ms_pending = false;  // ev1 recorded, elapsed time not read yet
     ConstTables C;
     GlobTables *hG = nullptr, *dG = nullptr;
     ScratchLayout L;
@@ -238,6 +239,7 @@ static void engine_init() {
     CK(cudaStreamCreate(&E.stream));
     CK(cudaEventCreate(&E.ev0));
     CK(cudaEventCreate(&E.ev1));
+    CK(cudaEventCreateWithFlags(&E.ev_err, cudaEventDisableTiming));
     E.hG = new GlobTables();
     build_tables(E.C, *E.hG);
     upload_const_tables(E.C);
@@ -602,7 +604,10 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
 }
 
 // do_single_step (speedy.f90:20-74) for one chunk of tiles
-static void run_model_step(const Ctx &c, bool any_daily, int *err_out, unsigned *masks) {
+// early_err (per-step driver call, last chunk): the error codes of the whole call are copied to the host right after the
+// diagnostics check, BEFORE the coupler kernel, and E.ev_err marks that copy: the host can hand the codes back to the caller
+// and launch the next step while the GPU finishes the land / sea models of this one.
+static void run_model_step(const Ctx &c, bool any_daily, int *err_out, unsigned *masks, int early_err_tiles = 0) {
     prof_mark(E.stream, -1);
     if (any_daily) {  // the daily forcing kernels read the flags of the step: set them first
         launch_control_pre(E.stream, c);
@@ -613,6 +618,10 @@ static void run_model_step(const Ctx &c, bool any_daily, int *err_out, unsigned 
     run_step_core(c, 2, 2, 2.0 * H_DELT, FL(0.05), 2, -1, any_daily ? 0 : 1);
     // step counter, check_diagnostics, calendar, sticky error codes of the call (k_diag_final)
     launch_diag(E.stream, c, 2, E.L.diagp, 1, err_out, masks);
+    if (early_err_tiles) {
+        CK(cudaMemcpyAsync(E.h_err, E.d_err, (size_t)early_err_tiles * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaEventRecord(E.ev_err, E.stream));
+    }
     launch_couple(E.stream, c, 0);
     prof_mark(E.stream, PC_POST);
     COUNT(3);
@@ -687,13 +696,14 @@ static int graph_max_tiles() {
     }
     return v;
 }
-static void run_chunk_step(int t0, int ntc, bool any_daily) {
+// returns true if the error codes were copied to the host inside the step (early_err_tiles > 0 and an eager launch)
+static bool run_chunk_step(int t0, int ntc, bool any_daily, int early_err_tiles = 0) {
     Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);
     const bool use_graph = ntc <= graph_max_tiles() && !P.on && g_eager_done[any_daily ? 1 : 0];
     if (!use_graph) {
-        run_model_step(c, any_daily, E.d_err + t0 * TILE, E.d_masks + t0);
+        run_model_step(c, any_daily, E.d_err + t0 * TILE, E.d_masks + t0, early_err_tiles);
         g_eager_done[any_daily ? 1 : 0] = true;
-        return;
+        return early_err_tiles > 0;
     }
     const StepGraphKey key(E.st, E.scr, E.sst, E.d_tiles, E.d_masks, E.d_err, E.st_elems, E.sst_months, t0, ntc,
                            any_daily ? 1 : 0);
@@ -713,6 +723,7 @@ static void run_chunk_step(int t0, int ntc, bool any_daily) {
     }
     CK(cudaGraphLaunch(it->second.exec, E.stream));
     COUNT(it->second.launches);
+    return false;
 }
 
 // bind controls, run nsteps for the listed members; returns per-member first error
@@ -778,8 +789,10 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         const double t_s0 = now_us();
         bool any_daily = false;
         for (size_t q = 0; q < run.size(); q++) any_daily |= (member_of(run[q])->current_step % NSTEPS == 0);
+        bool early = false;
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
-            run_chunk_step(t0, std::min(E.chunk_tiles, nt - t0), any_daily);
+            const bool last_chunk = t0 + E.chunk_tiles >= nt;
+            early = run_chunk_step(t0, std::min(E.chunk_tiles, nt - t0), any_daily, (per_step_sync && last_chunk) ? nt : 0);
         }
         t_launch += now_us() - t_s0;
         for (size_t q = 0; q < run.size(); q++) member_of(run[q])->current_step += 1;
@@ -797,9 +810,13 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         if (readback) {
             // error codes: read back at most once a day in batched mode; the device keeps the first non-zero code of
             // every member and freezes a failed member for the rest of the call (k_diag_final)
-            CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             const double t_w0 = now_us();
-            CK(cudaStreamSynchronize(E.stream));
+            if (early) {
+                CK(cudaEventSynchronize(E.ev_err));  // the coupler kernel of this step may still be running
+            } else {
+                CK(cudaMemcpyAsync(E.h_err, E.d_err, nt * TILE * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+                CK(cudaStreamSynchronize(E.stream));
+            }
             t_wait += now_us() - t_w0;
             for (size_t q = 0; q < run.size(); q++) {
                 const int code = E.h_err[epos[q]];
@@ -816,9 +833,9 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         }
     }
     CK(cudaEventRecord(E.ev1, E.stream));
-    CK(cudaStreamSynchronize(E.stream));
+    E.last_ms_pending = true;  // read on demand (spdy_last_elapsed_ms): the per-step call does not wait for the step's tail
+    if (!per_step_sync) CK(cudaStreamSynchronize(E.stream));
     CK(cudaGetLastError());  // a rejected kernel launch is not reported by the synchronisation
-    CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
     if (any_failed) {
         // the device masks of the failed members were cleared: upload them again with the next call; in a multi-step call
         // the host mirrors ran ahead of a member that stopped at its failing step -- take them from the device
@@ -1029,7 +1046,15 @@ void spdy_last_call_host_us(double *out4) {
     API_LOCK;
     for (int i = 0; i < 4; i++) out4[i] = g_host_us[i];
 }
-float spdy_last_elapsed_ms(void) { API_LOCK; return E.last_ms; }
+float spdy_last_elapsed_ms(void) {
+    API_LOCK;
+    if (E.last_ms_pending) {
+        CK(cudaEventSynchronize(E.ev1));
+        CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+        E.last_ms_pending = false;
+    }
+    return E.last_ms;
+}
 long long spdy_kernel_launches(void) { API_LOCK; return g_launches; }
 
 int spdy_get_model_datetime(int64_t h, int *out) {

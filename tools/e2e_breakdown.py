@@ -44,7 +44,9 @@ import numpy as np  # noqa: E402
 us = np.zeros(4)
 lib.spdy_last_call_host_us(_driver._ptr(us))
 print("  host phases of the last parallel_step call (us): prologue %.0f, launches %.0f, wait %.0f, epilogue %.0f" % tuple(us))
-for label, cbs in (("ens.run, no callbacks", []), ("ens.run + DiagnosticCheck + EnsembleStatistics", [DiagnosticCheck(36), EnsembleStatistics(36)])):
+ens.mean_and_spread(), ens.check()  # first-call allocations of the output path
+for label, cbs in (("ens.run, no callbacks", []), ("ens.run + DiagnosticCheck + EnsembleStatistics", [DiagnosticCheck(36), EnsembleStatistics(36)]),
+                   ("ens.run + DiagnosticCheck + EnsembleStatistics", [DiagnosticCheck(36), EnsembleStatistics(36)])):
     ens.current_date = end - a.steps * timedelta(seconds=2400)
     ms, _ = timed(lambda: ens.run(callbacks=cbs))
     print(f"{label:48s} {ms / a.steps:8.3f} ms/step")
