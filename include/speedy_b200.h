@@ -52,6 +52,10 @@ int spdy_shape(int64_t state, int var, int *dims /* [5] */, int *ndim);
  * non-zero code of each member (0 if none).  Returns the number of failed members. */
 int spdy_run_steps(const int64_t *states, const int64_t *controls, int n_members, int nsteps, int *error_codes);
 int spdy_reserve(int n_members);            /* pre-size the device arenas */
+/* SPPT, stochastically perturbed parametrisation tendencies (sppt.f90:40-146, physics.f90:233-248; the reference's
+ * compile-time switch params.f90:44, off by default here as there): per-member AR(1) pattern, counter-based generator */
+int spdy_set_sppt(int on, unsigned long long seed);
+int spdy_debug_get_sppt(int64_t state, double *spec /* (31,32,8) complex */, double *grid /* (96,48,8) */, long long *calls);
 int spdy_set_device(int ordinal);           /* select the GPU (before the first state is created) */
 int spdy_device_count(void);                /* CUDA devices visible to this process (0 without a driver) */
 int spdy_synchronize(void);

@@ -353,5 +353,19 @@ void orc_couple(void *st, void *ctl, int day) {
     couple_sea_atm(*(State *)st, day, c);
 }
 void orc_advance_date(void *ctl) { ((Control *)ctl)->advance_date(); }
+// SPPT switch of one member (sppt.f90; see gen_sppt): counter-based generator keyed by (seed, member id)
+void orc_set_sppt(void *st, int on, unsigned long long seed, unsigned long long member) {
+    State &s = *(State *)st;
+    s.sppt_on = on != 0, s.sppt_seed = seed, s.sppt_member = member, s.sppt_calls = 0;
+    s.sppt_spec.clear();
+}
+// the member's AR(1) pattern in spectral space (mx,nx,kx complex) and the grid-point pattern of the last step (ix,il,kx)
+int orc_get_sppt(void *st, double *spec, double *grid) {
+    State &s = *(State *)st;
+    if (s.sppt_spec.empty() || s.sppt_last.empty()) return -1;
+    memcpy(spec, s.sppt_spec.data(), sizeof(cplx) * s.sppt_spec.size());
+    memcpy(grid, s.sppt_last.data(), sizeof(double) * s.sppt_last.size());
+    return 0;
+}
 
 }  // extern "C"

@@ -63,6 +63,8 @@ def lib():
         L.orc_tendencies.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.orc_raw_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_implicit_terms.argtypes = [C.c_void_p] * 4
+        L.orc_set_sppt.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_ulonglong]
+        L.orc_get_sppt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_apply_tendencies.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 5
         L.orc_set_time_step.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -305,6 +307,16 @@ class State:
         """Horizontal diffusion + leapfrog / RAW filter of time_stepping.f90:78-144 for given tendencies."""
         t = [np.array(a, dtype=np.complex128, order="F", copy=True) for a in (vordt, divdt, tdt, psdt, trdt)]
         lib().orc_apply_tendencies(C.c_void_p(self.h), j1, float(dt), *[_ptr(a) for a in t])
+
+    def set_sppt(self, on, seed=0, member=0):
+        lib().orc_set_sppt(C.c_void_p(self.h), int(on), int(seed), int(member))
+
+    def sppt(self):
+        """(spectral AR(1) pattern (31,32,8) complex, grid-point pattern of the last step (96,48,8)), Fortran order."""
+        spec = np.zeros((MX, NX, KX), dtype=np.complex128, order="F")
+        grid = np.zeros((IX, IL, KX), order="F")
+        assert lib().orc_get_sppt(C.c_void_p(self.h), _ptr(spec), _ptr(grid)) == 0
+        return spec, grid
 
     def raw_step(self, j1, j2, dt):
         lib().orc_raw_step(C.c_void_p(self.h), j1, j2, float(dt))

@@ -740,9 +740,63 @@ void get_vertical_diffusion_tend(G3 se, G3 rh, G3 qa, G3 qsat, G3 phi, const int
 
 // ---------------------------------------------------------------------------------------------------
 // physics.f90:14-101 : spectral -> grid part, then the column physics proper
+// ---------------------------------------------------------------------------------------------------
+// sppt.f90:40-146 -- stochastically perturbed parametrisation tendencies (Palmer et al. 2009).
+// The reference routine cannot run as written: `sigma` is allocated (ix,il,kx) and assigned an (mx,nx) array, the AR(1)
+// state `sppt_spec` is a local allocatable that is freed at every return (so `phi * sppt_spec` reads unallocated memory),
+// the result is deallocated before it is returned, and the generator is seeded from the system clock.  This restates the
+// ALGORITHM those lines describe (the one of the routine's origin, speedy.f90 by S. Hatfield, where sigma and sppt_spec
+// are (mx,nx,kx) module arrays): complex Gaussian noise clipped to +-10, sigma(m,n) = f0 exp(-L^2 el2 / 4), AR(1) with
+// phi = exp(-(24/nsteps)/6 h), spec2grid, clipping to +-1 -- with the pattern kept per member and a counter-based
+// generator (splitmix64) in place of random_number, so that runs are reproducible and the GPU kernel can be compared.
+uint64_t sppt_mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// sppt.f90:118-133 randn(0, 1): Box-Muller with the reference's constants ((-2 log r1)**0.5, v = 2.0*6.28318530718 * r2
+// in REAL(4), sin); r1 in (0, 1], r2 in [0, 1) from the counter `ctr`
+static double sppt_randn(uint64_t key, uint64_t ctr) {
+    const double r1 = ((double)(sppt_mix64(key + 2 * ctr) >> 11) + 1.0) * 0x1p-53;
+    const double r2 = (double)(sppt_mix64(key + 2 * ctr + 1) >> 11) * 0x1p-53;
+    const double u = pow(-2.0 * log(r1), 0.5);
+    const double v = (double)(2.0f * 6.28318530718f) * r2;
+    return 0.0 + 1.0 * u * sin(v);
+}
+void gen_sppt(State &s, G3 sppt_grid) {
+    const double time_decorr = 6.0, len_decorr = 500000.0, stddev = FL(0.33);  // :27-37
+    const double phi = exp(-(24 / (double)nsteps) / time_decorr);
+    if (s.sppt_spec.empty()) s.sppt_spec.assign((size_t)mx * nx * kx, cplx{0.0, 0.0});
+    const uint64_t key = sppt_mix64(s.sppt_seed ^ sppt_mix64(s.sppt_member));
+    double f0 = 0.0;  // :87-88
+    for (int n = 1; n <= trunc_; n++) f0 = f0 + (2 * n + 1) * exp(-0.5 * ((len_decorr / rearth) * (len_decorr / rearth)) * n * (n + 1));
+    f0 = sqrt((stddev * stddev * (1 - phi * phi)) / (2 * f0));
+    const double first_fac = pow(1 - phi * phi, -0.5);
+    for (int k = 1; k <= kx; k++)
+        for (int n = 1; n <= nx; n++)
+            for (int m = 1; m <= mx; m++) {
+                const uint64_t ctr = (s.sppt_calls * (uint64_t)(mx * nx) + (uint64_t)((m - 1) + mx * (n - 1))) * kx + (k - 1);
+                const double rr = sppt_randn(key, 2 * ctr), ri = sppt_randn(key, 2 * ctr + 1);
+                const cplx eta = {fmin(10.0, fabs(rr)) * copysign(1.0, rr), fmin(10.0, fabs(ri)) * copysign(1.0, ri)};  // :73-76
+                const double sigma = f0 * exp(-0.25 * (len_decorr * len_decorr) * s.spec.el2[Spectral::i2(m, n)]);     // :90-92
+                cplx &x = s.sppt_spec[(m - 1) + (size_t)mx * ((n - 1) + (size_t)nx * (k - 1))];
+                if (s.sppt_calls == 0) x = (first_fac * sigma) * eta;  // :95
+                else x = phi * x + sigma * eta;                   // :100
+            }
+    s.sppt_calls += 1;
+    for (int k = 1; k <= kx; k++)
+        s.spec.spec2grid(S2{s.sppt_spec.data() + (size_t)mx * nx * (k - 1), mx}, sppt_grid.slab(k), 1);
+    for (size_t q = 0; q < NG * kx; q++) sppt_grid.p[q] = fmin(1.0, fabs(sppt_grid.p[q])) * copysign(1.0, sppt_grid.p[q]);  // :109
+}
+
 void get_physical_tendencies(State &s, int j1, G3 utend, G3 vtend, G3 ttend, G3 qtend) {
     const Spectral &sp = s.spec;
     Grid3 ug, vg, tg, qg, phig;
+    Grid3 utend_dyn, vtend_dyn, ttend_dyn, qtend_dyn;  // physics.f90:80-83
+    if (s.sppt_on)
+        for (size_t q = 0; q < NG * kx; q++)
+            utend_dyn.d[q] = utend.p[q], vtend_dyn.d[q] = vtend.p[q], ttend_dyn.d[q] = ttend.p[q], qtend_dyn.d[q] = qtend.p[q];
     Spec2 ucos, vcos;
     Grid2 pslg;
     S3 vor = s.s4lev(V_vor, j1), div = s.s4lev(V_div, j1), t = s.s4lev(V_t, j1), tr = s.s4lev(V_tr, j1),
@@ -757,6 +811,18 @@ void get_physical_tendencies(State &s, int j1, G3 utend, G3 vtend, G3 ttend, G3 
     }
     sp.spec2grid(s.s3lev(V_ps, j1), pslg, 1);
     physics_columns(s, ug, vg, tg, qg, phig, pslg, utend, vtend, ttend, qtend, nullptr);
+    if (s.sppt_on) {  // physics.f90:233-248 (mu(k) = 1, sppt.f90:20)
+        Grid3 pat;
+        gen_sppt(s, pat);
+        s.sppt_last = pat.d;
+        const double mu = 1.0;
+        for (size_t q = 0; q < NG * kx; q++) {
+            utend.p[q] = (1 + pat.d[q] * mu) * (utend.p[q] - utend_dyn.d[q]) + utend_dyn.d[q];
+            vtend.p[q] = (1 + pat.d[q] * mu) * (vtend.p[q] - vtend_dyn.d[q]) + vtend_dyn.d[q];
+            ttend.p[q] = (1 + pat.d[q] * mu) * (ttend.p[q] - ttend_dyn.d[q]) + ttend_dyn.d[q];
+            qtend.p[q] = (1 + pat.d[q] * mu) * (qtend.p[q] - qtend_dyn.d[q]) + qtend_dyn.d[q];
+        }
+    }
 }
 
 // physics.f90:103-231 : grid-point (column-independent) part.  qg is modified in place (max(qg,0)).

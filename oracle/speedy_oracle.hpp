@@ -242,6 +242,12 @@ struct State {
     Geometry geo;
     Spectral spec;
     Implicit imp;
+    // SPPT (sppt.f90; a compile-time switch in the reference, params.f90:44: off).  The AR(1) pattern is kept per member
+    // (the reference keeps ONE module-level pattern and loses it between calls: see gen_sppt in physics.cpp)
+    bool sppt_on = false;
+    uint64_t sppt_seed = 0, sppt_member = 0, sppt_calls = 0;  // calls of gen_sppt so far: noise counter, 0 = first AR(1) step
+    std::vector<cplx> sppt_spec;   // (mx, nx, kx)
+    std::vector<double> sppt_last; // (ix, il, kx) pattern of the last call (for tests)
 
     State();
     void alloc_sst_anom(int n_months_);
@@ -286,6 +292,8 @@ void set_orog_land_sfc_drag(G2 phi0, G2 forog);
 void get_vertical_diffusion_tend(G3 se, G3 rh, G3 qa, G3 qsat, G3 phi, const int *icnv, G3 utenvd, G3 vtenvd,
                                  G3 ttenvd, G3 qtenvd, const Geometry &g);
 void get_physical_tendencies(State &s, int j1, G3 utend, G3 vtend, G3 ttend, G3 qtend);
+void gen_sppt(State &s, G3 sppt_grid);
+uint64_t sppt_mix64(uint64_t z);
 void physics_columns(State &s, G3 ug, G3 vg, G3 tg, G3 qg, G3 phig, G2 pslg, G3 utend, G3 vtend, G3 ttend, G3 qtend,
                      int *dbg);
 

@@ -25,3 +25,9 @@ def example_sst_anomaly_file():
 
 
 from .speedy import Speedy, SpeedyEns, MODEL_STATE_DEF  # noqa
+
+
+def set_sppt(on, seed=0):
+    """Switch SPPT (stochastically perturbed parametrisation tendencies, speedy.f90/sppt.f90) on or off for every model
+    instance of this process -- the run-time form of the reference's compile-time ``sppt_on`` (params.f90:44)."""
+    return _speedy.set_sppt(on, seed)

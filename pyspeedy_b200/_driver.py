@@ -62,6 +62,8 @@ def lib():
         L.spdy_set.argtypes = [i64, ci, vp, C.c_size_t]
         L.spdy_shape.argtypes = [i64, ci, vp, vp]
         L.spdy_reserve.argtypes = [ci]
+        L.spdy_set_sppt.argtypes = [ci, C.c_ulonglong]
+        L.spdy_debug_get_sppt.argtypes = [i64, vp, vp, vp]
         L.spdy_set_device.argtypes = [ci]
         L.spdy_last_elapsed_ms.restype = C.c_float
         L.spdy_kernel_launches.restype = C.c_longlong
@@ -196,6 +198,12 @@ class _SpeedyDriver:
         err = np.zeros(s.shape[0], dtype=np.int32)
         lib().spdy_run_steps(_ptr(s), _ptr(c), s.shape[0], int(nsteps), _ptr(err))
         return err
+
+    @staticmethod
+    def set_sppt(on, seed=0):
+        """SPPT switch (the reference's compile-time ``sppt_on``, params.f90:44); applies to every member stepped from
+        now on.  Pattern generator keyed by (seed, member slot, patterns generated so far)."""
+        return int(lib().spdy_set_sppt(int(bool(on)), int(seed)))
 
     # ---- ensemble extensions (no reference counterpart)
     @staticmethod

@@ -73,7 +73,11 @@ ScratchLayout make_scratch_layout() {
     L.sfwd = take((long long)NSP * 80);
     L.four = take((long long)NFOUR * 80);
     L.diagp = take(2ll * KX * (MX - 1));
-    L.total = o;
+    L.total_base = o;
+    // SPPT fields at the end: part of the arena only while SPPT is switched on (spdy_set_sppt)
+    L.spptg = take(G3), L.tdyn = take(G3), L.qdyn = take(G3), L.udyn8 = take(NG), L.vdyn8 = take(NG);
+    L.total_sppt = o;
+    L.total = L.total_base;
     return L;
 }
 
@@ -109,7 +113,7 @@ struct Engine {
     double *st = nullptr, *sst = nullptr, *scr = nullptr;
     long long st_elems = 0, sst_elems = 0;
     int cap_tiles = 0, sst_months = 0, scr_tiles = 0, chunk_tiles = 64;
-    long long off[SPDY_NVARS], nelem[SPDY_NVARS], off_tcorh = 0, off_qcorh = 0, off_slots = 0;
+    long long off[SPDY_NVARS], nelem[SPDY_NVARS], off_tcorh = 0, off_qcorh = 0, off_slots = 0, off_sppt = 0;
     // handles
     std::vector<Member> members;
     std::vector<Control> controls;
@@ -123,7 +127,9 @@ struct Engine {
     std::vector<int> cached_tiles;
     std::vector<unsigned> cached_masks;
     // transform descriptor lists
-    InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2
+    InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2 (77 fields; 85 with the SPPT pattern levels appended)
+    bool sppt_on = false;
+    unsigned long long sppt_seed = 0;
     FwdDesc *d_fwd[FM_NMODES] = {};
     FwdDesc *d_fwd_all = nullptr;  // all fields of the step in one list (FwdDesc::mode set), two-operand modes first
     int n_fwd_all = 0;
@@ -147,7 +153,7 @@ static Ctx make_ctx(const int *d_tiles, const unsigned *d_masks, int ntiles) {
     c.st = E.st, c.scr = E.scr, c.sst = E.sst, c.tiles = d_tiles, c.masks = d_masks, c.G = E.dG;
     c.st_elems = E.st_elems, c.scr_elems = E.L.total, c.sst_elems = E.sst_elems;
     for (int v = 0; v < SPDY_NVARS; v++) c.off[v] = E.off[v];
-    c.off_tcorh = E.off_tcorh, c.off_qcorh = E.off_qcorh, c.off_slots = E.off_slots;
+    c.off_tcorh = E.off_tcorh, c.off_qcorh = E.off_qcorh, c.off_slots = E.off_slots, c.off_sppt = E.off_sppt;
     c.ntiles = ntiles, c.sst_months = E.sst_months;
     return c;
 }
@@ -173,6 +179,8 @@ static void build_descriptor_lists() {
         add(REF_SCR | L.ucosp8, L.pug8, 2);
         add(REF_SCR | L.vcosp8, L.pvg8, 2);
         add(E.off[V_ps], L.pslg, 1);
+        // SPPT pattern (used only when switched on: the list is then launched with 85 instead of 77 fields)
+        for (int k = 0; k < KX; k++) add(E.off_sppt + (long long)k * NSP, L.spptg + (long long)k * NG, 1);
         CK(cudaMalloc(&E.d_inv[j2 - 1], v.size() * sizeof(InvDesc)));
         CK(cudaMemcpy(E.d_inv[j2 - 1], v.data(), v.size() * sizeof(InvDesc), cudaMemcpyHostToDevice));
     }
@@ -261,6 +269,7 @@ static void engine_init() {
     E.off_tcorh = o, o += NSP;
     E.off_qcorh = o, o += NSP;
     E.off_slots = o, o += SL_COUNT;
+    E.off_sppt = o, o += (long long)NSP * KX;  // SPPT AR(1) pattern of the member (sppt.cu)
     E.st_elems = o;
     E.sst_elems = 0;
     const char *ct = getenv("SPDY_CHUNK_TILES");
@@ -584,8 +593,17 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
     launch_preops(E.stream, c, L, j2, fused_transforms() ? 1 : 0, with_control);
     COUNT(1);
     prof_mark(E.stream, PC_PREOPS);
-    run_inverse(c, E.d_inv[j2 - 1], 77);
-    if (fuse_dyn_physics()) {  // one kernel: the column's dynamical tendencies stay in registers (physics.cu)
+    if (E.sppt_on) launch_sppt_update(E.stream, c, E.sppt_seed), COUNT(1);
+    run_inverse(c, E.d_inv[j2 - 1], E.sppt_on ? 85 : 77);
+    if (E.sppt_on) {  // sppt.cu: three small kernels around the (untouched) physics kernel
+        launch_grid_dyn(E.stream, c, L);
+        prof_mark(E.stream, PC_GRID_DYN);
+        launch_sppt_save(E.stream, c, L);
+        launch_physics(E.stream, c, L, nullptr);
+        launch_sppt_apply(E.stream, c, L);
+        prof_mark(E.stream, PC_PHYSICS);
+        COUNT(4);
+    } else if (fuse_dyn_physics()) {  // one kernel: the column's dynamical tendencies stay in registers (physics.cu)
         prof_mark(E.stream, PC_GRID_DYN);
         launch_dyn_physics(E.stream, c, L);
         prof_mark(E.stream, PC_PHYSICS);
@@ -1063,6 +1081,45 @@ int spdy_get_model_datetime(int64_t h, int *out) {
     if (!m) return -1;
     const int s[5] = {SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE};
     for (int i = 0; i < 5; i++) out[i] = (int)get_slot_host(*m, s[i]);
+    return 0;
+}
+
+// SPPT switch (a compile-time constant of the reference: params.f90:44 `sppt_on`); applies to every member stepped from
+// now on.  The pattern generator is keyed by (seed, member slot, calls so far), see sppt.cu.
+int spdy_set_sppt(int on, unsigned long long seed) {
+    API_LOCK;
+    engine_init();
+    const bool want = on != 0;
+    E.sppt_seed = seed;
+    if (want != E.sppt_on) {  // the scratch arena carries the SPPT fields only while the switch is on
+        CK(cudaStreamSynchronize(E.stream));
+        E.sppt_on = want;
+        E.L.total = want ? E.L.total_sppt : E.L.total_base;
+        if (E.scr) CK(cudaFree(E.scr));
+        E.scr = nullptr, E.scr_tiles = 0;
+        drop_step_graphs();
+        E.cached_handles.clear();
+    }
+    return 0;
+}
+// the member's spectral AR(1) pattern ((31,32,8) complex) and the clipped grid-point pattern of its last single-member
+// step ((96,48,8)); calls = patterns generated so far
+int spdy_debug_get_sppt(int64_t h, double *spec, double *grid, long long *calls) {
+    API_LOCK;
+    Member *m = member_of(h);
+    if (!m || !E.sppt_on || !E.scr) return -1;
+    auto down = [&](double *dst, double *arena, long long te, int tile, long long off, long long n) {
+        for (long long o = 0; o < n; o += (long long)E.stage_elems) {
+            const long long cn = std::min<long long>(E.stage_elems, n - o);
+            k_gather<<<(int)((cn + 255) / 256), 256, 0, E.stream>>>(arena, te, tile, m->lane, off + o, cn, E.d_stage);
+            CK(cudaMemcpyAsync(E.h_stage, E.d_stage, cn * 8, cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            memcpy(dst + o, E.h_stage, cn * 8);
+        }
+    };
+    down(spec, E.st, E.st_elems, m->tile, E.off_sppt, (long long)NSP * KX);
+    down(grid, E.scr, E.L.total, 0, E.L.spptg, (long long)NG * KX);
+    *calls = (long long)get_slot_host(*m, SL_SPPT_CALLS);
     return 0;
 }
 

@@ -27,6 +27,7 @@ enum Slot {
     SL_STEP = 0, SL_YEAR, SL_MONTH, SL_DAY, SL_HOUR, SL_MINUTE, SL_MONTH_IDX, SL_IMONT1, SL_TMONTH, SL_TYEAR,
     SL_CO2, SL_CO2REF, SL_INCCO2, SL_SW, SL_LANDCPL, SL_SSTACPL, SL_ERR, SL_NMONTHS, SL_INITIALIZED, SL_DAILY,
     SL_CPLSTAMP, SL_CPLDIRTY,  // coupler climatology cache (surface.cu: k_couple)
+    SL_SPPT_CALLS,             // SPPT patterns generated for this member so far (noise counter; 0: first AR(1) step)
     SL_COUNT = 32
 };
 
@@ -75,6 +76,8 @@ struct GlobTables {
         vddym[NSPC], vddyp[NSPC], dmp[NSPC], dmpd[NSPC], dmps[NSPC];
     double gradx[MX];
     double fband[301 * 4];
+    double sppt_sigma[NSPC];  // sppt.f90:87-92: f0 * exp(-len_decorr^2 el2 / 4)
+    double sppt_phi, sppt_first_fac;  // AR(1) coefficient (:30), (1 - phi^2)^(-1/2) (:95)
     ImplTables impl[3];
 };
 
@@ -93,6 +96,7 @@ struct Ctx {
     long long st_elems, scr_elems, sst_elems;  // doubles per lane per tile
     long long off[SPDY_NVARS];                 // element offset of each registry variable
     long long off_tcorh, off_qcorh, off_slots; // extra per-member state
+    long long off_sppt;                        // SPPT AR(1) pattern, (mx,nx,kx) complex
     int ntiles;
     int sst_months;                            // slabs per member in the sst arena
 };
@@ -145,7 +149,9 @@ struct ScratchLayout {
     // Fourier fields (62 x 48)
     long long four;                                  // max(77, 73) fields
     long long diagp;                                 // partial sums of the diagnostics check
-    long long total;
+    long long total;                                 // doubles per lane in use (total_base, or total_sppt when SPPT is on)
+    // SPPT (allocated only while it is switched on): pattern on the grid, copies of the dynamical tendencies
+    long long spptg, tdyn, qdyn, udyn8, vdyn8, total_base, total_sppt;
 };
 ScratchLayout make_scratch_layout();
 

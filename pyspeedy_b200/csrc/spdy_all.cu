@@ -6,5 +6,6 @@
 #include "dynamics.cu"
 #include "physics.cu"
 #include "surface.cu"
+#include "sppt.cu"
 #include "tables.cu"
 #include "engine.cu"

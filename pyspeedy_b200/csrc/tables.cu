@@ -340,6 +340,7 @@ void build_tables(ConstTables &C, GlobTables &G) {
             }
             if (toff != PD2_TTOT) abort();
         }
+        // ---- SPPT amplitude spectrum (sppt.f90:27-37,87-95); filled after el2 below
         // ---- spectral operator tables (spectral.f90:68-110)
         const double re2 = H_REARTH * H_REARTH;
         for (int n = 0; n < NX; n++)
@@ -362,6 +363,17 @@ void build_tables(ConstTables &C, GlobTables &G) {
                 G.uvdyp[q] = -H_REARTH * E(m, n + 1) / (el1 + 1.0);
                 G.vddyp[q] = el1 * E(m, n + 1) / H_REARTH;
             }
+        // ---- SPPT amplitude spectrum and AR(1) constants (sppt.f90:27-37,87-95)
+        {
+            const double time_decorr = 6.0, len_decorr = 500000.0, stddev = FL(0.33);
+            const double phi = exp(-(24 / (double)NSTEPS) / time_decorr);
+            double f0 = 0.0;
+            for (int n = 1; n <= NTRUNC; n++)
+                f0 = f0 + (2 * n + 1) * exp(-0.5 * ((len_decorr / H_REARTH) * (len_decorr / H_REARTH)) * n * (n + 1));
+            f0 = sqrt((stddev * stddev * (1 - phi * phi)) / (2 * f0));
+            for (int q = 0; q < NSPC; q++) G.sppt_sigma[q] = f0 * exp(-0.25 * (len_decorr * len_decorr) * G.el2[q]);
+            G.sppt_phi = phi, G.sppt_first_fac = pow(1 - phi * phi, -0.5);
+        }
     }
     // ---- horizontal diffusion (horizontal_diffusion.f90:76-108)
     {
