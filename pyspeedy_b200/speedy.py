@@ -46,15 +46,46 @@ def _add_months(date, months):
 
 
 def _load_bc(bc_file):
+    """Boundary-condition fields by name: ``.npz`` (converted files) or NetCDF-4 like the reference's example_bc.nc
+    (pyspeedy/speedy.py:277: ``xr.load_dataset``); without xarray + netCDF4 the NetCDF-4 file is read by the package's
+    own HDF5 reader, which returns the same values (``_FillValue`` decoding as xarray does it)."""
     if bc_file.endswith(".npz"):
         with np.load(bc_file) as f:
             return {k: f[k] for k in f.files}
     try:
         import xarray as xr
-    except ImportError as exc:  # pragma: no cover
-        raise RuntimeError("NetCDF boundary files need xarray + netCDF4; use an .npz file in this image.") from exc
-    ds = xr.load_dataset(bc_file, engine="netcdf4")
-    return {k: ds[k].values for k in ds.data_vars}
+
+        ds = xr.load_dataset(bc_file, engine="netcdf4")
+        return {k: ds[k].values for k in ds.data_vars}
+    except ImportError:
+        from pyspeedy_b200 import hdf5_reader
+
+        return hdf5_reader.load(bc_file)
+
+
+def _load_ssta_nc(path):
+    """(months as 'YYYY-MM' strings, ssta (lon, lat, time)) of a NetCDF-4 SST anomaly file (variable ``ssta``, CF time
+    axis ``<unit> since <date>``), read with the package's HDF5 reader."""
+    from pyspeedy_b200 import hdf5_reader
+
+    f = hdf5_reader._File(path)
+    links = f.links(f.root)
+    if "ssta" not in links or "time" not in links:
+        raise RuntimeError(f"{path}: no 'ssta' / 'time' variable")
+    units = f.attributes(links["time"]).get("units")
+    if units is None:
+        raise RuntimeError(f"{path}: the time axis has no (fixed-length string) 'units' attribute")
+    unit, _, epoch = bytes(units).decode().strip("\0 ").partition(" since ")
+    fmt = "%Y-%m-%d %H:%M:%S" if ":" in epoch else "%Y-%m-%d"
+    base = datetime.strptime(epoch.strip()[:19], fmt)
+    if unit not in ("days", "hours", "minutes", "seconds"):
+        raise NotImplementedError(f"time unit '{unit}'")
+    t = f.dataset(links["time"]).astype(np.float64)
+    months = [(base + timedelta(**{unit: float(x)})).strftime("%Y-%m") for x in t]
+    ssta = hdf5_reader.load(path)["ssta"]
+    if ssta.shape[-1] != len(months):  # (time, lat, lon) on file -> (lon, lat, time)
+        ssta = np.transpose(ssta, (2, 1, 0))
+    return months, ssta
 
 
 class Speedy:
@@ -216,16 +247,19 @@ class Speedy:
         elif isinstance(sst_anomaly, str):
             if not os.path.isfile(sst_anomaly):
                 raise RuntimeError("The SST anomaly file does not exist.\n" f"File: {sst_anomaly}")
-            with np.load(sst_anomaly) as f:
-                months = [str(m) for m in f["time"]]
-                wanted = [_add_months(start_date, i).strftime("%Y-%m") for i in range(expected_months)]
-                missing = [w for w in wanted if w not in months]
-                if missing:
-                    raise RuntimeError(
-                        f"{len(missing)} months are missing in the SST anomalies file for the period: "
-                        + start_date.strftime("%Y/%m/%d") + " , " + end_date.strftime("%Y/%m/%d") + ".\n "
-                    )
-                ssta = np.stack([f["ssta"][:, :, months.index(w)] for w in wanted], axis=-1)
+            if sst_anomaly.endswith(".npz"):
+                with np.load(sst_anomaly) as f:
+                    months, field = [str(m) for m in f["time"]], f["ssta"]
+            else:
+                months, field = _load_ssta_nc(sst_anomaly)
+            wanted = [_add_months(start_date, i).strftime("%Y-%m") for i in range(expected_months)]
+            missing = [w for w in wanted if w not in months]
+            if missing:
+                raise RuntimeError(
+                    f"{len(missing)} months are missing in the SST anomalies file for the period: "
+                    + start_date.strftime("%Y/%m/%d") + " , " + end_date.strftime("%Y/%m/%d") + ".\n "
+                )
+            ssta = np.stack([field[:, :, months.index(w)] for w in wanted], axis=-1)
         elif isinstance(sst_anomaly, np.ndarray):
             ssta = sst_anomaly
             if ssta.shape != (96, 48, expected_months):

@@ -176,3 +176,36 @@ def test_coefficients_outside_the_truncation(oracle):
     st.spectral2grid()
     for v in ("u_grid", "v_grid", "t_grid", "q_grid", "phi_grid", "ps_grid"):
         assert relerr(m[v], st[v]) < 1e-10, (v, relerr(m[v], st[v]))
+
+
+def test_missing_value_markers_do_not_reach_the_model(tmp_path):
+    """The reference's example_bc.nc marks missing land / sea values with the netCDF default fill 9.96921e36 (its _FillValue
+    attribute is NaN, so xarray -- and pyspeedy_b200.hdf5_reader -- hand those numbers to the model), the packaged .npz marks
+    them NaN.  Every marker lies outside the land / sea masks, where initialisation overwrites the fields: a member
+    initialised from either file is the same model, bit for bit."""
+    import os
+
+    from pyspeedy_b200 import Speedy, _driver, _speedy, example_bc_file
+
+    bc = dict(np.load(example_bc_file()))
+    n_nan = 0
+    for k, v in bc.items():
+        n_nan += int(np.isnan(v).sum())
+        bc[k] = np.where(np.isnan(v), np.float32(9.96921e36), v).astype(v.dtype)
+    assert n_nan > 1000
+    path = os.path.join(tmp_path, "bc_fill.npz")
+    np.savez(path, **bc)
+    a = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    a.set_bc()
+    b = Speedy(start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    b.set_bc(bc_file=path)
+    for _ in range(3):
+        assert _speedy.step(a._state_cnt, a._control_cnt) == 0 and _speedy.step(b._state_cnt, b._control_cnt) == 0
+    for e in _driver.REGISTRY:
+        if e["shape"] is None or e["dtype"] not in ("f8", "c16") or e["name"] == "sst_anom":
+            continue
+        x, y = a[e["name"]], b[e["name"]]
+        if e["name"] in [v for v, _ in (("stl12", 0), ("snowd12", 0), ("soil_wc_l1", 0), ("soil_wc_l2", 0), ("soil_wc_l3", 0),
+                                        ("sst12", 0), ("sea_ice_frac12", 0))]:
+            continue  # the raw input climatologies keep whatever marker the file had
+        assert np.array_equal(x, y, equal_nan=True), e["name"]

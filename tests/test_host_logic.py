@@ -111,3 +111,35 @@ def test_fortran_shim_in_sync_with_registry(tmp_path):
         assert "subroutine is_array_%s(" % e["name"] in before
         if e["shape"] is not None:
             assert "subroutine get_%s_shape(" % e["name"] in before
+
+
+def test_hdf5_reader_on_the_reference_boundary_file():
+    """pyspeedy_b200.hdf5_reader (used by Speedy.set_bc(bc_file="*.nc") when xarray / netCDF4 are absent) on the reference's
+    own NetCDF-4 file: every variable of pyspeedy/data/example_bc.nc equals the packaged .npz conversion (which marks the
+    netCDF default fill value as NaN; the file's _FillValue attribute is NaN, so xarray -- and this reader -- keep the
+    9.96921e36 markers, all of which lie outside the land / sea masks: test_oracle_golden.py).  Runs where the reference is
+    mounted (this container); the GPU box has no /root/reference."""
+    import pytest
+
+    from pyspeedy_b200 import hdf5_reader
+    from pyspeedy_b200.speedy import _load_bc
+
+    src = "/root/reference/pyspeedy/data/example_bc.nc"
+    if not os.path.isfile(src):
+        pytest.skip("reference not mounted")
+    d = _load_bc(src)
+    ref = np.load(os.path.join(ROOT, "pyspeedy_b200", "data", "example_bc.npz"))
+    assert set(ref.files) <= set(d) and {"lon", "lat", "time"} <= set(d)
+    fill = np.float32(9.96921e36)
+    for k in ref.files:
+        a = d[k].copy()
+        assert a.dtype == np.float32 and a.shape == ref[k].shape
+        a[a == fill] = np.nan
+        assert np.array_equal(a, ref[k], equal_nan=True), k
+    assert d["lat"].shape == (48,) and abs(d["lat"][0] + 87.159) < 1e-3 and d["lon"][1] == 3.75
+    f = hdf5_reader._File(src)
+    att = f.attributes(f.links(f.root)["sst"])
+    assert bytes(att["long_name"]).startswith(b"sea-sfc. temperature") and np.isnan(att["_FillValue"]).all()
+    # the NetCDF-3 fixtures of the reference are not HDF5: a clear error, not garbage
+    with pytest.raises(ValueError):
+        hdf5_reader.load("/root/reference/pyspeedy/tests/fixtures/1982-01-02_0000.nc")
