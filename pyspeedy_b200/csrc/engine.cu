@@ -129,6 +129,7 @@ struct Engine {
     // transform descriptor lists
     InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2 (77 fields; 85 with the SPPT pattern levels appended)
     bool sppt_on = false;
+    int diag_out = 1;  // Ctx::diag_out of the step being launched (step_members)
     unsigned long long sppt_seed = 0;
     FwdDesc *d_fwd[FM_NMODES] = {};
     FwdDesc *d_fwd_all = nullptr;  // all fields of the step in one list (FwdDesc::mode set), two-operand modes first
@@ -154,7 +155,7 @@ static Ctx make_ctx(const int *d_tiles, const unsigned *d_masks, int ntiles) {
     c.st_elems = E.st_elems, c.scr_elems = E.L.total, c.sst_elems = E.sst_elems;
     for (int v = 0; v < SPDY_NVARS; v++) c.off[v] = E.off[v];
     c.off_tcorh = E.off_tcorh, c.off_qcorh = E.off_qcorh, c.off_slots = E.off_slots, c.off_sppt = E.off_sppt;
-    c.ntiles = ntiles, c.sst_months = E.sst_months;
+    c.ntiles = ntiles, c.sst_months = E.sst_months, c.diag_out = E.diag_out;
     return c;
 }
 
@@ -512,7 +513,10 @@ static bool fuse_dyn_physics() {
 }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     if (fused_transforms()) {  // parity-pure DMMA over latitude octets + two-stage FFT, Fourier rows stay in shared memory
-        launch_spec2grid_mma3(E.stream, c, d, n);
+        static const int gen = getenv("SPDY_S2G") ? atoi(getenv("SPDY_S2G")) : 4;
+        if (gen >= 5) launch_spec2grid_mma5(E.stream, c, d, n);
+        else if (gen == 4) launch_spec2grid_mma4(E.stream, c, d, n);
+        else launch_spec2grid_mma3(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
         return;
@@ -697,7 +701,7 @@ struct StepGraph {
     long long launches = 0;
 };
 typedef std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, long long, int, int,
-                   int, int>
+                   int, int, int>
     StepGraphKey;
 static std::map<StepGraphKey, StepGraph> g_step_graphs;
 static bool g_eager_done[2] = {false, false};  // statics inside the launchers are initialised by an eager run
@@ -724,7 +728,7 @@ static bool run_chunk_step(int t0, int ntc, bool any_daily, int early_err_tiles 
         return early_err_tiles > 0;
     }
     const StepGraphKey key(E.st, E.scr, E.sst, E.d_tiles, E.d_masks, E.d_err, E.st_elems, E.sst_months, t0, ntc,
-                           any_daily ? 1 : 0);
+                           any_daily ? 1 : 0, E.diag_out);
     auto it = g_step_graphs.find(key);
     if (it == g_step_graphs.end()) {
         StepGraph sg;
@@ -753,6 +757,8 @@ static inline double now_us() {
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
+static const bool g_profile_intermediate = getenv("SPDY_PROFILE_INTERMEDIATE") && atoi(getenv("SPDY_PROFILE_INTERMEDIATE")) != 0;
+static const bool g_lazy_diag = !(getenv("SPDY_LAZY_DIAG") && atoi(getenv("SPDY_LAZY_DIAG")) == 0);
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {
     engine_init();
     const double t_entry = now_us();
@@ -808,6 +814,11 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         bool any_daily = false;
         for (size_t q = 0; q < run.size(); q++) any_daily |= (member_of(run[q])->current_step % NSTEPS == 0);
         bool early = false;
+        // outputs of the column physics that no kernel reads (fluxes, precipitation, rad_flux, rad_st4a: 39 of the ~160
+        // doubles a column moves per step) are stored by the LAST step of a multi-step call only: nothing can observe the
+        // values the intermediate steps would have left there (tests/test_model_gpu.py::test_run_steps_equals_single_steps)
+        E.diag_out = (per_step_sync || s == nsteps - 1 || !g_lazy_diag) ? 1 : 0;
+        if (P.on && g_profile_intermediate) E.diag_out = 0;  // spdy_profile_step timing an intermediate step (bench.py)
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
             const bool last_chunk = t0 + E.chunk_tiles >= nt;
             early = run_chunk_step(t0, std::min(E.chunk_tiles, nt - t0), any_daily, (per_step_sync && last_chunk) ? nt : 0);
@@ -850,6 +861,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
                 if (err_out[idx[q]] == 0) advance_host_date(*ctl[q]);
         }
     }
+    E.diag_out = 1;
     CK(cudaEventRecord(E.ev1, E.stream));
     E.last_ms_pending = true;  // read on demand (spdy_last_elapsed_ms): the per-step call does not wait for the step's tail
     if (!per_step_sync) CK(cudaStreamSynchronize(E.stream));

@@ -26,6 +26,27 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// Two FFT lines per thread (the same latitude, two neighbouring members): the generated butterfly items (fft96_gen.cuh) are
+// templates on the value type, and with D2 every shared-memory access of an FFT warp is 128 bits wide -- half the LDS /
+// STS instructions per line and two independent dependency chains per thread.
+struct __align__(16) D2 {
+    double x, y;
+};
+__device__ __forceinline__ D2 operator+(const D2 a, const D2 b) { return D2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ D2 operator-(const D2 a, const D2 b) { return D2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ D2 operator-(const D2 a) { return D2{-a.x, -a.y}; }
+__device__ __forceinline__ D2 operator*(const double s, const D2 a) { return D2{s * a.x, s * a.y}; }
+__device__ __forceinline__ D2 operator*(const D2 a, const double s) { return D2{a.x * s, a.y * s}; }
+struct LdSlot2 {  // stage-A loader for a pair of members: Fourier row r of a slot
+    const double *p;
+    __device__ __forceinline__ D2 operator()(int r) const { return *reinterpret_cast<const D2 *>(p + r * MQ_NM); }
+};
+struct StExch2 {  // in-place stage-B store for a pair of lines (see StExchK), optional 1/cos(lat) factor
+    D2 *p;
+    double sc;
+    bool scale;
+    __device__ __forceinline__ void operator()(int i, D2 v) const { p[(i >> 3) * 32] = scale ? v * sc : v; }
+};
 struct LdSlot {  // FFT stage-A loader: Fourier row r of a slot, this thread's member
     const double *p;
     __device__ __forceinline__ double operator()(int r) const { return p[r * MQ_NM]; }
@@ -45,12 +66,18 @@ struct StExchK {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static const CUtensorMap &s2g2_tensor_map(const Ctx &c) {
+// nlat = latitude rows per box: 4 (quad per hemisphere) or 8 (octet per hemisphere)
+static const CUtensorMap &s2g2_tensor_map(const Ctx &c, const int nlat = 4) {
     static EncodeTiledFn encode = nullptr;
-    static CUtensorMap map;
-    static const void *k_scr = nullptr;
-    static long long k_elems = -1;
-    static int k_tiles = -1;
+    static CUtensorMap maps[2];
+    static const void *ks_scr[2] = {nullptr, nullptr};
+    static long long ks_elems[2] = {-1, -1};
+    static int ks_tiles[2] = {-1, -1};
+    const int slot = nlat == 8 ? 1 : 0;
+    CUtensorMap &map = maps[slot];
+    const void *&k_scr = ks_scr[slot];
+    long long &k_elems = ks_elems[slot];
+    int &k_tiles = ks_tiles[slot];
     if (!encode) {
         cudaDriverEntryPointQueryResult qr;
         void *fn = nullptr;
@@ -63,7 +90,7 @@ static const CUtensorMap &s2g2_tensor_map(const Ctx &c) {
     if (k_scr != c.scr || k_elems != c.scr_elems || k_tiles != c.ntiles) {
         const cuuint64_t dims[5] = {(cuuint64_t)TILE, (cuuint64_t)IL, 12, 8, (cuuint64_t)c.ntiles * (cuuint64_t)c.scr_elems};
         const cuuint64_t strides[4] = {(cuuint64_t)IX * TILE * 8, 8ull * TILE * 8, (cuuint64_t)TILE * 8, (cuuint64_t)TILE * 8};
-        const cuuint32_t box[5] = {MQ_NM, 4, 12, 8, 1}, estr[5] = {1, 1, 1, 1, 1};
+        const cuuint32_t box[5] = {MQ_NM, (cuuint32_t)nlat, 12, 8, 1}, estr[5] = {1, 1, 1, 1, 1};
         const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, c.scr, dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
 #pragma unroll
         for (int k = 0; k < KX; k++) sm[(5 * KX + k) * 128] = tsum[k];
     }
-    if (act) {
+    const bool dg = act && c.diag_out;  // outputs nothing reads before the next step overwrites them (Ctx::diag_out)
+    if (dg) {
         *ST2D(V_cbmf) = cbmf;
         *ST2D(V_precnv) = precnv;
         *ST2D(V_precls) = precls;
@@ -609,14 +610,19 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         evap3 = evap2 + fmask * (evap1 - evap2);
         slru3 = slru2 + fmask * (slru1 - slru2);
         ts = tsea + fmask * (land_temp - tsea);
-        if (act) {
+        if (act) {  // the land / sea models (surface.cu) read hfluxn, shf(sea), evap(sea)
+            double *p;
+            p = ST2D(V_shf), p[lev] = shf2;
+            p = ST2D(V_evap), p[lev] = evap2;
+            p = ST2D(V_hfluxn), p[0] = hfl1, p[lev] = hfl2;
+        }
+        if (dg) {
             double *p;
             p = ST2D(V_ustr), p[0] = ustr1, p[lev] = ustr2, p[2 * lev] = ustr3;
             p = ST2D(V_vstr), p[0] = vstr1, p[lev] = vstr2, p[2 * lev] = vstr3;
-            p = ST2D(V_shf), p[0] = shf1, p[lev] = shf2, p[2 * lev] = shf3;
-            p = ST2D(V_evap), p[0] = evap1, p[lev] = evap2, p[2 * lev] = evap3;
+            p = ST2D(V_shf), p[0] = shf1, p[2 * lev] = shf3;
+            p = ST2D(V_evap), p[0] = evap1, p[2 * lev] = evap3;
             p = ST2D(V_slru), p[0] = slru1, p[lev] = slru2, p[2 * lev] = slru3;
-            p = ST2D(V_hfluxn), p[0] = hfl1, p[lev] = hfl2;
             *ST2D(V_slrd) = slrd;
         }
     }
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         double olr = corlw1 + corlw2;
 #pragma unroll
         for (int jb = 0; jb < 4; jb++) olr = olr + flux[jb];
-        if (act) {
+        if (dg) {
             *ST2D(V_slr) = slr;
             *ST2D(V_olr) = olr;
             double *pf = ST2D(V_rad_flux), *ps4 = ST2D(V_rad_st4a);

@@ -99,6 +99,9 @@ struct Ctx {
     long long off_sppt;                        // SPPT AR(1) pattern, (mx,nx,kx) complex
     int ntiles;
     int sst_months;                            // slabs per member in the sst arena
+    int diag_out;                              // 0: an intermediate step of a multi-step driver call -- the column physics
+                                               // does not store the outputs that the NEXT step overwrites before anything on
+                                               // the device (or the host: the call has not returned) can read them
 };
 
 __device__ __forceinline__ double *stp(const Ctx &c, int t, long long off, int lane) {

@@ -2,6 +2,8 @@
 // without relocatable device code).  Build: see pyspeedy_b200/csrc/Makefile.
 #include "transforms.cu"
 #include "fused_mma3.cu"
+#include "fused_mma4.cu"
+#include "fused_mma5.cu"
 #include "fused_mma2.cu"
 #include "dynamics.cu"
 #include "physics.cu"

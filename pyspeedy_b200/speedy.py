@@ -438,29 +438,49 @@ class SpeedyEns:
             out[v] = mean_spread_from_sums(s1, s2, self.n_total)
         return out
 
-    def run(self, callbacks=None, steps_per_call=1):
+    def run(self, callbacks=None, steps_per_call=None):
         """Run every member between the start and end dates (pyspeedy/speedy.py:547-593).
 
-        ``steps_per_call > 1`` (extension) keeps the time loop on the device between callbacks."""
+        The reference calls every callback after every step; the stock callbacks return at once unless the step counter is
+        a multiple of their ``interval`` (``BaseCallback.skip_flag``, pyspeedy/callbacks.py:48-58).  With
+        ``steps_per_call=None`` (default) the loop uses that: when every callback derives from ``BaseCallback`` the
+        members are advanced by ONE multi-step driver call up to the next step at which some callback can act (at most a
+        simulated day per call), which is observably the same sequence of callback actions; any other callable gets the
+        reference's one driver call per step.  ``steps_per_call=n`` forces n steps per driver call (1 = the reference's
+        loop).  Inside a multi-step call a failing member is frozen at its failing step and reported when the call returns
+        (the per-step loop raises right after the failing step)."""
         if callbacks is None:
             callbacks = []
         end_date = self.members[0].end_date
         dt_step = timedelta(seconds=3600 * 24 / 36)
         state_cnts, control_cnts = self.handles()
         date_cnts = np.array([m._model_date for m in self], dtype=np.int64)  # noqa
+        intervals = None
+        if steps_per_call is None:
+            from pyspeedy_b200.callbacks import BaseCallback
+
+            if all(isinstance(cb, BaseCallback) for cb in callbacks):
+                intervals = [max(1, int(cb.interval)) for cb in callbacks]
+            else:
+                steps_per_call = 1
+        step = self.get_current_step() if intervals else 0
         while self.current_date < end_date:
-            if steps_per_call > 1:
-                left = int(round((end_date - self.current_date) / dt_step))
-                n = max(1, min(steps_per_call, left))
+            left = int(round((end_date - self.current_date) / dt_step))
+            if intervals is not None:
+                n = min([36] + [i - step % i for i in intervals])
+            else:
+                n = steps_per_call
+            n = max(1, min(n, left))
+            if n > 1:
                 error_codes = _speedy.run_steps(state_cnts, control_cnts, n)
-                self.current_date += n * dt_step
             else:
                 error_codes = _speedy.parallel_step(state_cnts, control_cnts)
-                self.current_date += dt_step
+            step += n
+            self.current_date += n * dt_step
             if (error_codes < 0).any():
                 msg = ""
-                for n, code in enumerate(error_codes):
-                    msg += f"Member{n}: {ERROR_CODES[code]}\n"
+                for k, code in enumerate(error_codes):
+                    msg += f"Member{k}: {ERROR_CODES[code]}\n"
                 raise RuntimeError(msg)
             # "update current date in all members" (pyspeedy/speedy.py:588-590): one driver call, the members' datetime
             # containers are updated in place

@@ -138,6 +138,57 @@ def test_run_loop_with_callbacks_matches_run_steps():
     assert np.abs(t.std(axis=0) - st.spread["t_grid"][1].T[::-1]).max() < 1e-3
 
 
+def test_multistep_call_leaves_the_complete_state():
+    """Intermediate steps of a multi-step driver call do not store the column-physics outputs that the next step overwrites
+    (Ctx::diag_out, physics.cu).  After the call EVERY registry variable must be what step-by-step driver calls leave --
+    including the short-wave diagnostics (tsr, ssr, qcloud_equiv) that only every third step writes: 8 steps end on a
+    long-wave-only step, so those come from an intermediate step of the call."""
+    from pyspeedy_b200 import MODEL_STATE_DEF, SpeedyEns, _speedy
+
+    e = SpeedyEns(4, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    e.set_bc()  # four identical members: 0, 1 take one multi-step call, 2, 3 eight per-step calls
+    s, c = e.handles()
+    assert (_speedy.run_steps(s[:2], c[:2], 8) == 0).all()
+    for _ in range(8):
+        assert (_speedy.parallel_step(s[2:], c[2:]) == 0).all()
+    checked = 0
+    for v in MODEL_STATE_DEF:
+        x, y = e.members[1][v], e.members[3][v]
+        assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True), v
+        checked += 1
+    assert checked >= 109
+    assert np.abs(e.members[1]["olr"]).max() > 0 and np.abs(e.members[1]["tsr"]).max() > 0
+
+
+def test_run_loop_batches_steps_between_callbacks():
+    """SpeedyEns.run keeps the time loop on the device up to the next step at which a callback can act (all callbacks
+    derive from BaseCallback: `interval`), and falls back to one driver call per step for a plain callable."""
+    from pyspeedy_b200 import SpeedyEns, _speedy
+    from pyspeedy_b200.callbacks import DiagnosticCheck, EnsembleStatistics
+
+    start, end = datetime(1982, 1, 1), datetime(1982, 1, 3)
+    calls = []
+    orig_run, orig_par = _speedy.run_steps, _speedy.parallel_step
+    _speedy.run_steps = lambda s, c, n: (calls.append(n), orig_run(s, c, n))[1]
+    _speedy.parallel_step = lambda s, c: (calls.append(1), orig_par(s, c))[1]
+    try:
+        a = SpeedyEns(3, start_date=start, end_date=end)
+        a.set_bc()
+        st = EnsembleStatistics(interval=36)
+        a.run(callbacks=[DiagnosticCheck(interval=24), st])
+        assert calls == [24, 12, 12, 24] and st.times == [start + timedelta(days=1), end]
+        calls.clear()
+        b = SpeedyEns(3, start_date=start, end_date=end)
+        b.set_bc()
+        seen = []
+        b.run(callbacks=[lambda m: seen.append(m.current_date)])
+        assert calls == [1] * 72 and len(seen) == 72
+    finally:
+        _speedy.run_steps, _speedy.parallel_step = orig_run, orig_par
+    for v in ("vor", "t", "tr", "olr"):
+        assert np.array_equal(a.members[2][v], b.members[2][v]), v
+
+
 def test_seeded_ensembles_are_reproducible_per_slot():
     """perturb_temperature is a counter-based generator keyed by (seed, arena slot): the same slots with the same seed
     evolve bit-identically whether stepped by run_steps or by the run loop."""

@@ -432,17 +432,18 @@ def emit(fname, args, outs, load_expr, store_stmt):
             name[n] = a
         elif op == "in":
             name[n] = "x%d" % n
-            lines.append("    const double x%d = %s;" % (n, load_expr(a)))
+            lines.append("    const T x%d = %s;" % (n, load_expr(a)))
         elif op == "neg":
             name[n] = "(-%s)" % name[a]
         else:
             sym = {"add": "+", "sub": "-", "mul": "*"}[op]
             name[n] = "t%d" % n
-            lines.append("    const double t%d = %s %s %s;" % (n, name[a], sym, name[b]))
+            lines.append("    const T t%d = %s %s %s;" % (n, name[a], sym, name[b]))
             flops += 1
     for slot in sorted(outs):
         lines.append("    " + store_stmt(slot, name[outs[slot]]))
-    tmpl = "template <class LD> " if "LD ld" in args else "template <class ST> "
+    # T = value type: double (one line per thread) or a pair of lines (D2, fused_common.cuh: 128-bit shared-memory accesses)
+    tmpl = "template <class LD, class T> " if "LD ld" in args else "template <class T, class ST> "
     src = tmpl + "__device__ __forceinline__ void %s(%s) {\n%s\n}\n" % (fname, args, "\n".join(lines))
     return src, flops
 
@@ -452,7 +453,8 @@ def main():
     out = []
     out.append("// GENERATED by tools/gen_fft96.py -- do not edit.  See that script for the derivation.\n"
                "// 96-point real FFT pair equivalent to the reference's FFTPACK path (fftpack.f90:69-202 with the\n"
-               "// N=96 factorisation 2,4,4,3), as zero-pruned straight-line items.  FFT_LS = lane stride (doubles).\n"
+               "// N=96 factorisation 2,4,4,3), as zero-pruned straight-line items.  FFT_LS = lane stride (in values of type T:\n"
+               "// double, or a pair of lines).\n"
                "#pragma once\n")
     report = []
 
@@ -466,7 +468,7 @@ def main():
     report.append("inverse stage A items: " + str([len(c) for c in comps]))
     nA = len(comps)
     for q, slots in enumerate(comps):
-        src, fl = emit("fftb_A%d" % q, "const LD ld, double* __restrict__ s",
+        src, fl = emit("fftb_A%d" % q, "const LD ld, T* __restrict__ s",
                        {s: mid[s] for s in slots},
                        lambda a: "ld(%d)" % a[1],
                        lambda slot, v: "s[%d * FFT_LS] = %s;" % (slot, v))
@@ -478,7 +480,7 @@ def main():
     report.append("inverse stage B items: " + str([len(c) for c in comps]))
     nB = len(comps)
     for q, slots in enumerate(comps):
-        src, fl = emit("fftb_B%d" % q, "const double* __restrict__ s, const ST st",
+        src, fl = emit("fftb_B%d" % q, "const T* __restrict__ s, const ST st",
                        {s: fin[s] for s in slots},
                        lambda a: "s[%d * FFT_LS]" % a[1],
                        lambda slot, v: "st(%d, %s);" % (slot, v))
@@ -493,7 +495,7 @@ def main():
     report.append("forward stage A items: " + str([len(c) for c in comps]))
     nA = len(comps)
     for q, slots in enumerate(comps):
-        src, fl = emit("fftf_A%d" % q, "const LD ld, double* __restrict__ s",
+        src, fl = emit("fftf_A%d" % q, "const LD ld, T* __restrict__ s",
                        {s: mid[s] for s in slots},
                        lambda a: "ld(%d)" % a[1],
                        lambda slot, v: "s[%d * FFT_LS] = %s;" % (slot, v))
@@ -508,7 +510,7 @@ def main():
     report.append("forward stage B items: " + str([len(c) for c in comps]))
     nB = len(comps)
     for q, slots in enumerate(comps):
-        src, fl = emit("fftf_B%d" % q, "const double* __restrict__ s, const ST st",
+        src, fl = emit("fftf_B%d" % q, "const T* __restrict__ s, const ST st",
                        {s: keep[s] for s in slots},
                        lambda a: "s[%d * FFT_LS]" % a[1],
                        lambda slot, v: "st(%d, %s);" % (slot, v))
