@@ -180,6 +180,36 @@ __device__ __forceinline__ void raw_update_idle(double *p1, double *p2, const do
     if (act && __double_as_longlong(o2) != __double_as_longlong(a2)) *p2 = o2;
 }
 
+// Outside the triangular truncation the tendency is zero (trfilt), and the Robert-Asselin-Williams filter with a zero
+// tendency is the identity on a coefficient whose two time levels hold the same bits: (a - 2a) + a == 0 exactly, so both
+// levels keep a.  (Exceptions: -0, which the filter turns into +0, and NaN.)  That is the normal state of those rows -- zeros,
+// and in row m + n = 31 whatever grid2spectral left there at initialisation -- unless the host stored something else.  A
+// multi-step driver call therefore looks at them ONCE (here) and its spectral steps skip those rows for the tiles where
+// every active member passed (Ctx::outer_zero).  Two flags per tile, preset to non-zero: [2t] row m + n = 31 (a perturbed
+// ensemble set up like examples/Ensemble_forecast.ipynb -- grid2spectral writes time level 1 only -- keeps moving there),
+// [2t + 1] the 465 coefficients with m + n >= 32.
+__device__ __forceinline__ bool outer_moves(const double a1, const double a2) {
+    const long long b1 = __double_as_longlong(a1), b2 = __double_as_longlong(a2);
+    return b1 != b2 || b1 == (long long)0x8000000000000000ull || a1 != a1;
+}
+__global__ void __launch_bounds__(256) k_scan_outer(const Ctx c, int *__restrict__ flags) {
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y;
+    const int cc = w & 1, q = w >> 1;
+    if (q >= NSPC) return;
+    const int m = q % MX, n = q / MX;
+    if (m + n <= NTRUNC) return;
+    const size_t e = (size_t)(2 * m + cc + M2 * n) * TILE, lev = (size_t)NSP * TILE, tl = (size_t)KX * lev;
+    const double *vor = stp(c, t, c.off[V_vor], lane) + e, *dvs = stp(c, t, c.off[V_div], lane) + e,
+                 *tt = stp(c, t, c.off[V_t], lane) + e, *trs = stp(c, t, c.off[V_tr], lane) + e,
+                 *ps = stp(c, t, c.off[V_ps], lane) + e;
+    bool bad = outer_moves(ps[0], ps[lev]);
+#pragma unroll
+    for (int k = 0; k < KX; k++)
+        bad |= outer_moves(vor[k * lev], vor[tl + k * lev]) | outer_moves(dvs[k * lev], dvs[tl + k * lev]) |
+               outer_moves(tt[k * lev], tt[tl + k * lev]) | outer_moves(trs[k * lev], trs[tl + k * lev]);
+    if (lane_active(c, t, lane) && bad) flags[2 * t + (m + n > NTRUNC + 1)] = 0;
+}
+
 // Vorticity and tracer: no vertical coupling -> one thread per (coefficient, component, level)
 // (tendencies.f90:238-268 spectral part, time_stepping.f90:78-144)
 __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const ScratchLayout L, const int j1, const double dt,
@@ -201,6 +231,7 @@ __global__ void __launch_bounds__(256) k_spec_step_vq(const Ctx c, const Scratch
     // with a zero tendency, so their 8 tendency rows, the correction field and the damping tables are never loaded.
     const bool live = (m + n <= NTRUNC) || dump >= 0;
     if (!live) {
+        if (c.outer_zero && c.outer_zero[2 * t + (m + n > NTRUNC + 1)]) return;  // the filter is the identity here (k_scan_outer)
         const double v1 = *vor, q1 = *trs, v2 = vor[tl], q2 = trs[tl];
         raw_update_idle(vor, vor + tl, v1, v2, trf, j1, dt, eps, act);
         raw_update_idle(trs, trs + tl, q1, q2, trf, j1, dt, eps, act);
@@ -246,6 +277,7 @@ __global__ void __launch_bounds__(128) k_spec_step_dt(const Ctx c, const Scratch
     const double *phi = stp(c, t, c.off[V_phi], lane) + e;
     const double el2 = G->el2[q], trf = G->trfilt[q];
     if (m + n > NTRUNC && dump < 0) {  // outside the truncation: zero tendency, time filter only (see k_spec_step_vq)
+        if (c.outer_zero && c.outer_zero[2 * t + (m + n > NTRUNC + 1)]) return;
         double a1[2 * KX + 1], a2[2 * KX + 1];
 #pragma unroll
         for (int k = 0; k < KX; k++) {
@@ -555,6 +587,9 @@ void launch_spec_step(cudaStream_t s, const Ctx &c, const ScratchLayout &L, int 
     k_spec_step_vq<<<dim3(NSPC * 2 * KX / 8, c.ntiles), 256, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
     if (impl_idx == 2) k_spec_step_dt<true><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
     else k_spec_step_dt<false><<<dim3(NSPC * 2 / 4, c.ntiles), 128, 0, s>>>(c, L, j1, dt, eps, impl_idx, dump);
+}
+void launch_scan_outer(cudaStream_t s, const Ctx &c, int *flags) {
+    k_scan_outer<<<dim3(NSPC * 2 / 8, c.ntiles), 256, 0, s>>>(c, flags);
 }
 void launch_diag(cudaStream_t s, const Ctx &c, int time_lev, long long part, int mode, int *err_out = nullptr,
                  unsigned *masks = nullptr) {

@@ -130,6 +130,8 @@ struct Engine {
     InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2 (77 fields; 85 with the SPPT pattern levels appended)
     bool sppt_on = false;
     int diag_out = 1;  // Ctx::diag_out of the step being launched (step_members)
+    int *d_outer = nullptr;  // Ctx::outer_zero flags of the tiles of the current multi-step call (size err_cap / TILE)
+    bool outer_on = false;
     unsigned long long sppt_seed = 0;
     FwdDesc *d_fwd[FM_NMODES] = {};
     FwdDesc *d_fwd_all = nullptr;  // all fields of the step in one list (FwdDesc::mode set), two-operand modes first
@@ -156,6 +158,8 @@ static Ctx make_ctx(const int *d_tiles, const unsigned *d_masks, int ntiles) {
     for (int v = 0; v < SPDY_NVARS; v++) c.off[v] = E.off[v];
     c.off_tcorh = E.off_tcorh, c.off_qcorh = E.off_qcorh, c.off_slots = E.off_slots, c.off_sppt = E.off_sppt;
     c.ntiles = ntiles, c.sst_months = E.sst_months, c.diag_out = E.diag_out;
+    // the flags are indexed like the tile list of the call
+    c.outer_zero = (E.outer_on && d_tiles >= E.d_tiles) ? E.d_outer + 2 * (d_tiles - E.d_tiles) : nullptr;
     return c;
 }
 
@@ -700,8 +704,8 @@ struct StepGraph {
     cudaGraphExec_t exec = nullptr;
     long long launches = 0;
 };
-typedef std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, long long, int, int,
-                   int, int, int>
+typedef std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, const void *, long long,
+                   int, int, int, int, int>
     StepGraphKey;
 static std::map<StepGraphKey, StepGraph> g_step_graphs;
 static bool g_eager_done[2] = {false, false};  // statics inside the launchers are initialised by an eager run
@@ -727,8 +731,8 @@ static bool run_chunk_step(int t0, int ntc, bool any_daily, int early_err_tiles 
         g_eager_done[any_daily ? 1 : 0] = true;
         return early_err_tiles > 0;
     }
-    const StepGraphKey key(E.st, E.scr, E.sst, E.d_tiles, E.d_masks, E.d_err, E.st_elems, E.sst_months, t0, ntc,
-                           any_daily ? 1 : 0, E.diag_out);
+    const StepGraphKey key(E.st, E.scr, E.sst, E.d_tiles, E.d_masks, E.d_err, E.d_outer, E.st_elems, E.sst_months, t0, ntc,
+                           any_daily ? 1 : 0, E.diag_out + 2 * (E.outer_on ? 1 : 0));
     auto it = g_step_graphs.find(key);
     if (it == g_step_graphs.end()) {
         StepGraph sg;
@@ -758,6 +762,7 @@ static inline double now_us() {
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 static const bool g_profile_intermediate = getenv("SPDY_PROFILE_INTERMEDIATE") && atoi(getenv("SPDY_PROFILE_INTERMEDIATE")) != 0;
+static const bool g_scan_outer = !(getenv("SPDY_SCAN_OUTER") && atoi(getenv("SPDY_SCAN_OUTER")) == 0);
 static const bool g_lazy_diag = !(getenv("SPDY_LAZY_DIAG") && atoi(getenv("SPDY_LAZY_DIAG")) == 0);
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {
     engine_init();
@@ -786,9 +791,10 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     if (run.empty()) return failed;
     const int nt = prepare_members(run.data(), (int)run.size());
     if (nt * TILE > E.err_cap) {
-        if (E.d_err) CK(cudaFree(E.d_err)), CK(cudaFreeHost(E.h_err));
+        if (E.d_err) CK(cudaFree(E.d_err)), CK(cudaFreeHost(E.h_err)), CK(cudaFree(E.d_outer));
         E.err_cap = nt * TILE;
         CK(cudaMalloc(&E.d_err, E.err_cap * sizeof(int)));
+        CK(cudaMalloc(&E.d_outer, 2 * nt * sizeof(int)));
         CK(cudaMallocHost(&E.h_err, E.err_cap * sizeof(int)));
     }
     std::map<int, int> tile_pos;
@@ -808,6 +814,15 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     CK(cudaMemsetAsync(E.d_err, 0, (size_t)nt * TILE * sizeof(int), E.stream));  // sticky within this call (k_diag_final)
     bool any_failed = false;
     CK(cudaEventRecord(E.ev0, E.stream));
+    // multi-step call: look once at the coefficients outside the triangular truncation (k_scan_outer, dynamics.cu)
+    E.outer_on = false;
+    if (nsteps >= 4 && !per_step_sync && g_scan_outer) {
+        CK(cudaMemsetAsync(E.d_outer, 1, (size_t)2 * nt * sizeof(int), E.stream));  // bytes 0x01: non-zero = "all zero so far"
+        for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles)
+            launch_scan_outer(E.stream, make_ctx(E.d_tiles + t0, E.d_masks + t0, std::min(E.chunk_tiles, nt - t0)), E.d_outer + 2 * t0);
+        COUNT((nt + E.chunk_tiles - 1) / E.chunk_tiles);
+        E.outer_on = true;
+    }
     const double t_first = now_us();
     for (int s = 0; s < nsteps; s++) {
         const double t_s0 = now_us();
@@ -861,7 +876,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
                 if (err_out[idx[q]] == 0) advance_host_date(*ctl[q]);
         }
     }
-    E.diag_out = 1;
+    E.diag_out = 1, E.outer_on = false;
     CK(cudaEventRecord(E.ev1, E.stream));
     E.last_ms_pending = true;  // read on demand (spdy_last_elapsed_ms): the per-step call does not wait for the step's tail
     if (!per_step_sync) CK(cudaStreamSynchronize(E.stream));

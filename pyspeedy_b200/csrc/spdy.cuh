@@ -99,6 +99,9 @@ struct Ctx {
     long long off_sppt;                        // SPPT AR(1) pattern, (mx,nx,kx) complex
     int ntiles;
     int sst_months;                            // slabs per member in the sst arena
+    const int *outer_zero;                     // [2 * ntiles] or nullptr.  Non-zero: the time filter is the identity on every
+                                               // coefficient outside the triangular truncation (vor, div, t, tr, ps) of the
+                                               // tile's active members (k_scan_outer at the start of a multi-step call)
     int diag_out;                              // 0: an intermediate step of a multi-step driver call -- the column physics
                                                // does not store the outputs that the NEXT step overwrites before anything on
                                                // the device (or the host: the call has not returned) can read them

@@ -178,6 +178,49 @@ def test_coefficients_outside_the_truncation(oracle):
         assert relerr(m[v], st[v]) < 1e-10, (v, relerr(m[v], st[v]))
 
 
+def test_outside_coefficients_in_a_multistep_call():
+    """A multi-step driver call scans the coefficients outside the truncation once and its spectral steps skip them for tiles
+    where the time filter is the identity on all of them (both time levels bit-equal: k_scan_outer, dynamics.cu).  Same
+    final state as per-step calls (which never skip) in three cases: untouched members (skipped), a member with noise
+    stored in ONE time level in a tile of untouched ones (not skipped), and a stored -0 (the filter turns it into +0)."""
+    from pyspeedy_b200 import SpeedyEns, _speedy
+
+    e = SpeedyEns(6, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    e.set_bc()
+    s, c = e.handles()
+    assert (_speedy.parallel_step(s, c) == 0).all()
+    mm, nn = np.meshgrid(np.arange(31), np.arange(32), indexing="ij")
+    outside = (mm + nn) > 30
+    rng = np.random.default_rng(7)
+    x = np.array(e.members[0]["t"])
+    assert np.array_equal(x[outside][..., 0], x[outside][..., 1])  # the model itself keeps the two levels equal there
+    noisy = x.copy()
+    noisy[..., 0] += 1e-3 * (rng.standard_normal(x.shape[:3]) + 1j * rng.standard_normal(x.shape[:3])) * outside[:, :, None]
+    e.members[1]["t"] = noisy
+    e.members[4]["t"] = noisy
+    vz = np.array(e.members[2]["vor"])
+    vz[30, 31, 3, 0] = complex(-0.0, 0.0)
+    e.members[2]["vor"] = vz
+    e.members[5]["vor"] = vz
+    # members 0-2: one multi-step call; members 3-5 (same states): per-step calls
+    assert (_speedy.run_steps(s[:3], c[:3], 6) == 0).all()
+    for _ in range(6):
+        assert (_speedy.parallel_step(s[3:], c[3:]) == 0).all()
+    for k in range(3):
+        for v in PROG:
+            a, b = np.asarray(e.members[k][v]), np.asarray(e.members[k + 3][v])
+            assert a.tobytes() == b.tobytes(), (k, v)  # bit patterns: -0 vs +0 would show
+    assert np.abs(np.asarray(e.members[1]["t"])[outside]).max() > 0
+    # a clean ensemble on its own takes the skipping path: compare with the clean member of the mixed tile
+    f = SpeedyEns(2, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))
+    f.set_bc()
+    sf, cf = f.handles()
+    assert (_speedy.parallel_step(sf, cf) == 0).all()
+    assert (_speedy.run_steps(sf, cf, 6) == 0).all()
+    for v in PROG:
+        assert np.array_equal(np.asarray(f.members[1][v]), np.asarray(e.members[0][v])), v
+
+
 def test_missing_value_markers_do_not_reach_the_model(tmp_path):
     """The reference's example_bc.nc marks missing land / sea values with the netCDF default fill 9.96921e36 (its _FillValue
     attribute is NaN, so xarray -- and pyspeedy_b200.hdf5_reader -- hand those numbers to the model), the packaged .npz marks
