@@ -137,7 +137,7 @@ int spdy_batch_spec2grid(const double *spec, double *grid, int kcos, int n) {
     ws_set_kcos(kcos);
     ws_move(spec, nullptr, WS_SPEC, NSP, n);
     if (fused_transforms()) {
-        launch_spec2grid_mma3(E.stream, c, W.d_inv, 1);
+        launch_spec2grid_mma4(E.stream, c, W.d_inv, 1);
     } else {
         launch_legendre_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
         launch_fft_inv(E.stream, c, W.d_inv, 1, WS_FOUR);
@@ -266,7 +266,7 @@ int spdy_bench_spectral_chain(const double *vor, const double *dv, int npairs, i
         CK(cudaEventRecord(ev[0], E.stream));
         launch_uvspec(E.stream, c, REF_SCR | WS_SPEC, REF_SCR | WS_SPEC2, REF_SCR | WS_SPEC3, REF_SCR | WS_SPEC4, 1, 0);
         CK(cudaEventRecord(ev[1], E.stream));
-        launch_spec2grid_mma3(E.stream, c, W.d_inv2, 2);
+        launch_spec2grid_mma4(E.stream, c, W.d_inv2, 2);
         CK(cudaEventRecord(ev[2], E.stream));
         ws_forward2(c);
         CK(cudaEventRecord(ev[3], E.stream));

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(256) k_ens_reduce(const double *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------- kernel schedules
-// SPDY_FUSED selects the transform kernels: default = the fused kernels (spec -> grid: k_spec2grid_mma3, fused_mma3.cu;
+// SPDY_FUSED selects the transform kernels: default = the fused kernels (spec -> grid: k_spec2grid_mma4, fused_mma3.cu + fused_mma4.cu;
 // grid -> spec: ONE mixed-mode launch of k_grid2spec_mma2, fused_mma2.cu); SPDY_FUSED=0 = separate Legendre and FFT
 // kernels both ways (transforms.cu), kept as the unfused cross-check of the parity tests.
 static bool fused_transforms() {
@@ -517,10 +517,7 @@ static bool fuse_dyn_physics() {
 }
 static void run_inverse(const Ctx &c, const InvDesc *d, int n) {
     if (fused_transforms()) {  // parity-pure DMMA over latitude octets + two-stage FFT, Fourier rows stay in shared memory
-        static const int gen = getenv("SPDY_S2G") ? atoi(getenv("SPDY_S2G")) : 4;
-        if (gen >= 5) launch_spec2grid_mma5(E.stream, c, d, n);
-        else if (gen == 4) launch_spec2grid_mma4(E.stream, c, d, n);
-        else launch_spec2grid_mma3(E.stream, c, d, n);
+        launch_spec2grid_mma4(E.stream, c, d, n);
         prof_mark(E.stream, PC_FFT_INV);
         COUNT(1);
         return;
@@ -596,7 +593,7 @@ static void run_step_core(const Ctx &c, int j1, int j2, double dt, double eps, i
                           int with_control = 0) {
     const ScratchLayout &L = E.L;
     const long long tl2 = (long long)(j2 - 1) * NSP * KX;
-    // spectral pre-operators in one launch: geopotential (time level 1), uvspec, grad(ps).  k_spec2grid_mma3 reads the rows
+    // spectral pre-operators in one launch: geopotential (time level 1), uvspec, grad(ps).  k_spec2grid_mma4 reads the rows
     // inside the nsh2 mask only: uvspec and the gradient skip the other 47 % of each field
     launch_preops(E.stream, c, L, j2, fused_transforms() ? 1 : 0, with_control);
     COUNT(1);

@@ -6,7 +6,7 @@ namespace spdy {
 // Fused grid -> spectral transform (default path).  Reference semantics: fourier.f90:90-123
 // (+ fftpack.f90:136-202), legendre.f90:170-221, grid-point products of tendencies.f90:238-268 applied while loading.
 //
-// Mirror of k_spec2grid_mma3 (fused_mma3.cu):
+// Mirror of k_spec2grid_mma4 (fused_mma4.cu):
 //   * the grid rows of a hemisphere-quad (4 latitudes x 96 points x 8 members, 24 KB per operand field) arrive by ONE
 //     cp.async.bulk.tensor load per operand through the 5-D tensor map of fused_common.cuh, two passes ahead of
 //     their use (ring of three buffers, mbarrier completion): no F warp ever waits for a global load;

@@ -2,7 +2,7 @@
 //
 // Reference semantics: legendre.f90:130-168 (inverse Legendre), fourier.f90:63-88 + fftpack.f90:69-134 (inverse FFT).
 //
-// Same work decomposition, slots, exchange buffers, parity-pure DMMA k-slices and TMA tensor stores as k_spec2grid_mma3
+// Same work decomposition, slots, exchange buffers, parity-pure DMMA k-slices and TMA tensor stores as the round-1 kernel k_spec2grid_mma3
 // (fused_mma3.cu).  What changed is the split of the register file (ncu of mma3: the FFT warps are the bottleneck -- the
 // Legendre warps spend half their time waiting for an empty slot -- and their four-warp groups are badly balanced: the
 // seven stage-A items cost 24..96 flops, so the 2+2+2+1 split has a critical path of 192 flop units per pass against 96
@@ -88,7 +88,7 @@ __device__ __forceinline__ void s2g4_L(const Ctx &c, const InvDesc *__restrict__
 }
 
 // F warp fw of 12: hemisphere fw / 6, item share fw % 6; lane = (jl, member); two passes (halves of the hemisphere's eight
-// latitudes) per octet, slot rows, exchange buffers and the TMA store as in s2g3_F (fused_mma3.cu)
+// latitudes) per octet, slot rows, exchange buffers and the TMA store as in the round-1 kernel
 __device__ __forceinline__ void s2g4_F(const Ctx &c, const InvDesc *__restrict__ descs, const int nwork,
                                        const double *slots, double *exch, const CUtensorMap *tmap, const int fw,
                                        const int lane) {

@@ -3,7 +3,6 @@
 #include "transforms.cu"
 #include "fused_mma3.cu"
 #include "fused_mma4.cu"
-#include "fused_mma5.cu"
 #include "fused_mma2.cu"
 #include "dynamics.cu"
 #include "physics.cu"

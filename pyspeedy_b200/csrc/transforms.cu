@@ -339,7 +339,7 @@ __device__ __forceinline__ void uvspec_elem(const GlobTables *G, const double *v
 }
 
 // tri: the consumer is an inverse transform that reads the rows n <= 31 - m only (legendre.f90:143-158 through nsh2;
-// k_spec2grid_mma3 never touches the others), so the 465 coefficients beyond them are neither loaded nor stored
+// k_spec2grid_mma4 never touches the others), so the 465 coefficients beyond them are neither loaded nor stored
 __global__ void __launch_bounds__(128) k_uvspec(const Ctx c, FieldRef vor, FieldRef dv, FieldRef u, FieldRef v, int nlev,
                                                 int tri) {
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;

@@ -1,3 +1,7 @@
+// EXPERIMENT (round 2, NOT part of the library build): measured slower than the default kernel and kept for the record.
+// Result at 512 members, 77 fields (parity-green): 0.647 ms against 0.444 ms for k_spec2grid_mma4 (fused_mma4.cu): one
+// item per warp and stage leaves the 24..96-flop stage-A items unbalanced behind a 256-thread barrier, and 136 registers
+// for two lines per thread spill (192 bytes of stack).
 // speedy-b200: fifth-generation fused spectral -> grid transform: two FFT lines per thread.
 //
 // Reference semantics: legendre.f90:130-168 (inverse Legendre), fourier.f90:63-88 + fftpack.f90:69-134 (inverse FFT).
