@@ -12,12 +12,16 @@ grid-point noise (examples/Ensemble_forecast.ipynb cell 8).  A "step" is one mod
 
   value : whole-job throughput, state resident in HBM, K steps by one spdy_run_steps call per rank
   e2e   : the same K steps through the package's public run loop -- SpeedyEns.run(callbacks=[DiagnosticCheck,
-          EnsembleStatistics]) (pyspeedy/speedy.py:547-593): per step one parallel_step driver call with host handle
-          arrays in and per-member error codes out plus the batched date update; once per simulated day (and at the end of
-          the region) the batched diagnostics check and the ensemble mean/spread of the 6 default outputs (spectral2grid of
-          every member with the partial sums in its epilogue, NCCL all-reduce, one device-to-host copy)
-  roofline     : dominant kernel class of one step, algorithmic bytes / CUDA-event time vs the measured HBM peak, on a
-                 512-member launch from an idle GPU (burst peak) and in situ (full shard, hot clocks)
+          EnsembleStatistics]) (pyspeedy/speedy.py:547-593): the loop advances the members to the next step at which a
+          callback acts (one multi-step driver call with host handle arrays in and per-member error codes out, then the
+          batched date update); once per simulated day -- the region is aligned so that its last step is one of them -- the
+          batched diagnostics check and the ensemble mean/spread of the 6 default outputs (spectral2grid of every member
+          with the partial sums in its epilogue, NCCL all-reduce, one device-to-host copy)
+  roofline     : dominant kernel class of one step AS THE TIMED REGION RUNS IT (an intermediate step of a multi-step call:
+                 the column physics does not store the 39 doubles per column that nothing reads before the next step
+                 overwrites them), algorithmic bytes / CUDA-event time vs the measured HBM peak, on a 512-member launch
+                 from an idle GPU (burst peak) and in situ (full shard, hot clocks); `last_step` = the same for the step
+                 that stores everything (every step of a per-step driver call)
   cpu_baseline : the oracle (C++ restatement of the reference Fortran, which cannot be built in this image) driven like
                  parallel_step with OpenMP over members on all host cores, bounded sample
 --impl reference times that CPU path as the reference arm.  --config 1 / 2 / 4 / 5 run the other BASELINE configurations
@@ -66,6 +70,11 @@ ALG_BYTES = {
 ALG_FUSED = {"fft_inv": 77 * (SPEC_MASK_B + GRID_B), "legendre_inv": 0,
              "fft_fwd": (33 + 64) * GRID_B + 73 * SPEC_MASK_B, "legendre_dir": 0}
 PHYS_SW_B, PHYS_LW_B = 4608 * 167 * 8, 4608 * 158 * 8  # per member, short-wave / long-wave-only step
+# intermediate steps of a multi-step driver call (physics.cu, Ctx::diag_out): 39 doubles per column are not stored (cbmf,
+# precnv, precls, ustr/vstr/slru x3, shf/evap land + mean, slrd, slr, olr, rad_flux x4, rad_st4a x16)
+PHYS_LAZY_B = 4608 * 39 * 8
+# ... and (dynamics.cu, k_scan_outer) the 465 coefficients with m + n >= 32 of the 33 prognostic fields are not read
+SPEC_SKIP_B = 465 * 16 * 2 * 33
 
 
 def measured_peaks():
@@ -187,11 +196,13 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def roofline_of(prof, n_launch, peaks, peak_kind, label):
+def roofline_of(prof, n_launch, peaks, peak_kind, label, intermediate=False):
     """Per-class algorithmic GB/s of one instrumented step (class times `prof` in ms, `n_launch` members per launch)."""
     alg = dict(ALG_BYTES)
     if prof["legendre_inv"] == 0.0 and prof["legendre_dir"] == 0.0:
         alg.update(ALG_FUSED)
+    if intermediate:
+        alg["physics"] -= PHYS_LAZY_B
     cls = max(alg, key=lambda k: prof[k])
     total = sum(prof.values())
     achieved = alg[cls] * n_launch / (prof[cls] * 1e-3) / 1e9
@@ -206,12 +217,12 @@ def roofline_of(prof, n_launch, peaks, peak_kind, label):
     }
 
 
-def profile_mean(_speedy, s, c, reps=3):
+def profile_mean(_speedy, s, c, reps=3, intermediate=False):
     """Three consecutive instrumented steps = one short-wave step + two long-wave-only steps, averaged per class."""
-    _speedy.profile_step(s, c)
+    _speedy.profile_step(s, c, intermediate)
     prof = None
     for _ in range(reps):
-        p1, _ = _speedy.profile_step(s, c)
+        p1, _ = _speedy.profile_step(s, c, intermediate)
         prof = p1 if prof is None else {k: prof[k] + p1[k] for k in p1}
     return {k: v / reps for k, v in prof.items()}
 
@@ -259,29 +270,29 @@ def run_config3(args):
 
     # ---- end-to-end: the package's run loop with callbacks, exactly K steps -----------------------------------
     class DailyOutput(EnsembleStatistics):
-        """EnsembleStatistics once per simulated day counted from the start of the region, and at its last step."""
+        """EnsembleStatistics(interval=36) with the time spent in it; keeps only the latest statistics."""
 
-        def __init__(self, step0, last):
+        def __init__(self):
             super().__init__(interval=NSTEPS_DAY)
-            self.step0, self.last, self.seconds, self.calls = step0, last, 0.0, 0
-
-        def skip_flag(self, model):
-            k = model.get_current_step() - self.step0
-            return not (k % NSTEPS_DAY == 0 or k == self.last)
+            self.seconds, self.calls = 0.0, 0
 
         def __call__(self, model):
             if self.skip_flag(model):
                 return
             t1 = time.perf_counter()
             super().__call__(model)
-            self.times.clear()  # keep only the latest statistics: this is a benchmark, not a forecast archive
+            self.times.clear()  # this is a benchmark, not a forecast archive
             for v in self.variables:
                 del self.mean[v][:-1], self.spread[v][:-1]
             self.seconds += time.perf_counter() - t1
             self.calls += 1
 
+    # align the region: its LAST step is a multiple of 36 steps, so the daily callbacks act ceil(K / 36) times inside it
+    pad = (-(ens.get_current_step() + args.steps)) % NSTEPS_DAY
+    if pad:
+        assert (_speedy.run_steps(s, c, pad) == 0).all()
     ens.mean_and_spread(), ens.check()  # first-call allocations of the output path (sum buffers, pinned copies)
-    out = DailyOutput(ens.get_current_step(), args.steps)
+    out = DailyOutput()
     ens.current_date = end - args.steps * DT_STEP  # the loop variable of SpeedyEns.run: K steps to go
     comm.barrier()
     t0 = time.perf_counter()
@@ -291,32 +302,48 @@ def run_config3(args):
     comm.barrier()
     e2e_value = m_total * args.steps / NSTEPS_DAY / t_e2e
     stats_bytes = 2 * (5 * 96 * 48 * 8 + 96 * 48) * 8
-    h2d = int(s.nbytes + c.nbytes + s.nbytes + 20)  # state / control handle arrays + date containers and the date
-    d2h = int(4 * m_local + (out.calls * stats_bytes + 4 * m_local * max(1, args.steps // NSTEPS_DAY)) / args.steps)
+    n_calls = -(-args.steps // NSTEPS_DAY)  # driver calls of the run loop: one per callback interval
+    # per driver call: state / control handle arrays in, error codes out; per output time: date containers + date in,
+    # statistics and the codes of the batched check out
+    h2d = int(((s.nbytes + c.nbytes) * n_calls + (s.nbytes + 20) * n_calls) / args.steps)
+    d2h = int((4 * m_local * n_calls + out.calls * (stats_bytes + 4 * m_local)) / args.steps)
 
     # ---- roofline of the dominant kernel class ------------------------------------------------------------------
     # (a) in situ: one instrumented step of the whole shard right after the timed regions (power-capped clocks, launches
     #     of up to 2048 members); (b) one 512-member launch from an idle GPU, the figure comparable with the burst HBM
     #     number of MEASURED_PEAKS.json
     peaks, peak_kind = measured_peaks()
-    prof_hot = profile_mean(_speedy, s, c)
     chunk = min(m_local, 2048)
-    hot = roofline_of({k: v * chunk / m_local for k, v in prof_hot.items()}, chunk, peaks, peak_kind, "in situ (hot clocks)")
+    prof_hot = profile_mean(_speedy, s, c, intermediate=True)
+    hot = roofline_of({k: v * chunk / m_local for k, v in prof_hot.items()}, chunk, peaks, peak_kind, "in situ (hot clocks)", True)
     time.sleep(2.0)
     n_prof = min(m_local, 512)
-    idle = roofline_of(profile_mean(_speedy, s[:n_prof], c[:n_prof]), n_prof, peaks, peak_kind, "idle GPU, one launch")
+    idle = roofline_of(profile_mean(_speedy, s[:n_prof], c[:n_prof], intermediate=True), n_prof, peaks, peak_kind,
+                       "idle GPU, one launch", True)
+    last = roofline_of(profile_mean(_speedy, s[:n_prof], c[:n_prof]), n_prof, peaks, peak_kind, "idle GPU, one launch")
     traffic, tfile = ncu_traffic(n_prof)
     alg = idle.pop("_alg")
+    alg_last = last.pop("_alg")
     hot.pop("_alg")
     per_class_traffic = {k: traffic[k] for k in alg if k in traffic and idle["per_class_ms"].get(k, 0) > 0}
+    # what the timed region moved per step (intermediate steps; the spectral step also skips the rows k_scan_outer cleared)
+    timed_alg = sum(alg.values()) - SPEC_SKIP_B + (PHYS_LAZY_B / args.steps)
     roofline = {
         "bound": "hbm", "kernel": idle["kernel"], "achieved": idle["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": idle["frac"], "traffic": traffic.get(idle["kernel"]), "peak_kind": peak_kind, **idle,
+        "frac": idle["frac"], "traffic": traffic.get(idle["kernel"]), "peak_kind": peak_kind,
+        "variant": "intermediate step of a multi-step driver call (what the timed region runs)", **idle,
         "per_class_traffic_bytes": per_class_traffic, "traffic_source": tfile,
         "traffic_over_algorithmic": {k: round(v / (alg[k] * n_prof), 3) for k, v in per_class_traffic.items() if alg[k]},
+        "last_step": {"variant": "step that stores every output (last step of a call; every per-step driver call)",
+                      "kernel": last["kernel"], "achieved": last["achieved"], "frac": last["frac"],
+                      "algorithmic_bytes_per_launch": last["algorithmic_bytes_per_launch"],
+                      "ms": last["per_class_ms"][last["kernel"]], "traffic": traffic.get(last["kernel"] + "_last_step"),
+                      "step_algorithmic_gbs": last["step_algorithmic_gbs"]},
         "in_situ": {k: hot[k] for k in ("kernel", "achieved", "frac", "members_per_launch", "per_class_ms", "per_class_gbs",
                                         "step_algorithmic_gbs", "when")},
+        "timed_region_algorithmic_gbs": timed_alg * m_local / (dev_ms_max / args.steps * 1e-3) / 1e9,
     }
+    del alg_last
 
     if rank != 0:
         comm.destroy()

@@ -114,6 +114,9 @@ int spdy_batch_spectral2grid(const int64_t *states, int n);      /* transform_sp
 /* one step with CUDA events between kernel classes: ms[10] = forcing, pre-ops, legendre_inv, fft_inv, grid_dyn,
  * physics, fft_fwd, legendre_dir, spec_step, post (first chunk of 16 tiles is instrumented) */
 int spdy_profile_step(const int64_t *states, const int64_t *controls, int n, float *ms, int *error_codes);
+/* on != 0: spdy_profile_step times the step as an INTERMEDIATE step of a multi-step call runs it (the column physics does
+ * not store the outputs that nothing reads before the next step overwrites them; extension, see spdy_run_steps) */
+int spdy_profile_intermediate(int on);
 
 /* ---- stage-level entry points (parity tests, microbenchmarks); host buffers, one field after another -------- */
 int spdy_table(const char *name, double *dst, int cap);

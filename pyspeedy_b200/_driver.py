@@ -98,6 +98,7 @@ def lib():
         L.spdy_perturb_temperature.argtypes = [vp, ci, C.c_ulonglong, C.c_double]
         L.spdy_batch_spectral2grid.argtypes = [vp, ci]
         L.spdy_profile_step.argtypes = [vp, vp, ci, vp, vp]
+        L.spdy_profile_intermediate.argtypes = [ci]
         L.spdy_debug_physics.argtypes = [i64] + [vp] * 11
         L.spdy_debug_raw_step.argtypes = [i64, ci, ci, ci]
         L.spdy_debug_get_corh.argtypes = [i64, vp, vp]
@@ -287,12 +288,16 @@ class _SpeedyDriver:
         return err
 
     @staticmethod
-    def profile_step(state_containers, control_containers):
+    def profile_step(state_containers, control_containers, intermediate=False):
+        """One instrumented step: ms per kernel class.  ``intermediate``: timed the way a multi-step call runs its
+        intermediate steps (column-physics outputs that nothing reads before the next step are not stored)."""
+        lib().spdy_profile_intermediate(1 if intermediate else 0)
         s = np.ascontiguousarray(state_containers, dtype=np.int64)
         c = np.ascontiguousarray(control_containers, dtype=np.int64)
         ms = np.zeros(10, dtype=np.float32)
         err = np.zeros(s.shape[0], dtype=np.int32)
         lib().spdy_profile_step(_ptr(s), _ptr(c), s.shape[0], _ptr(ms), _ptr(err))
+        lib().spdy_profile_intermediate(0)
         names = ["forcing", "pre_ops", "legendre_inv", "fft_inv", "grid_dyn", "physics", "fft_fwd", "legendre_dir",
                  "spec_step", "post"]
         return dict(zip(names, (float(x) for x in ms))), err

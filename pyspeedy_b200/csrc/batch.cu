@@ -411,6 +411,11 @@ int spdy_batch_spectral2grid(const int64_t *hs, int n) {
     CK(cudaStreamSynchronize(E.stream));
     return 0;
 }
+int spdy_profile_intermediate(int on) {
+    API_LOCK;
+    g_profile_intermediate = on != 0;
+    return 0;
+}
 // one model step of the listed members with device events between kernel classes; ms[10] per class (summed over chunks):
 // forcing, pre-ops, legendre_inv, fft_inv, grid_dyn, physics, fft_fwd, legendre_dir, spec_step, post
 int spdy_profile_step(const int64_t *hs, const int64_t *cs, int n, float *ms, int *err) {

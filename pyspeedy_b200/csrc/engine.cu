@@ -758,7 +758,7 @@ static inline double now_us() {
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
-static const bool g_profile_intermediate = getenv("SPDY_PROFILE_INTERMEDIATE") && atoi(getenv("SPDY_PROFILE_INTERMEDIATE")) != 0;
+static bool g_profile_intermediate = getenv("SPDY_PROFILE_INTERMEDIATE") && atoi(getenv("SPDY_PROFILE_INTERMEDIATE")) != 0;
 static const bool g_scan_outer = !(getenv("SPDY_SCAN_OUTER") && atoi(getenv("SPDY_SCAN_OUTER")) == 0);
 static const bool g_lazy_diag = !(getenv("SPDY_LAZY_DIAG") && atoi(getenv("SPDY_LAZY_DIAG")) == 0);
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {

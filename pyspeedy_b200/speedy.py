@@ -459,7 +459,8 @@ class SpeedyEns:
         if steps_per_call is None:
             from pyspeedy_b200.callbacks import BaseCallback
 
-            if all(isinstance(cb, BaseCallback) for cb in callbacks):
+            # a subclass that replaces skip_flag may act at any step: only the stock test (step % interval) is batched over
+            if all(isinstance(cb, BaseCallback) and type(cb).skip_flag is BaseCallback.skip_flag for cb in callbacks):
                 intervals = [max(1, int(cb.interval)) for cb in callbacks]
             else:
                 steps_per_call = 1
