@@ -203,6 +203,7 @@ def roofline_of(prof, n_launch, peaks, peak_kind, label, intermediate=False):
         alg.update(ALG_FUSED)
     if intermediate:
         alg["physics"] -= PHYS_LAZY_B
+        alg["spec_step"] -= SPEC_SKIP_B
     cls = max(alg, key=lambda k: prof[k])
     total = sum(prof.values())
     achieved = alg[cls] * n_launch / (prof[cls] * 1e-3) / 1e9
@@ -327,7 +328,7 @@ def run_config3(args):
     hot.pop("_alg")
     per_class_traffic = {k: traffic[k] for k in alg if k in traffic and idle["per_class_ms"].get(k, 0) > 0}
     # what the timed region moved per step (intermediate steps; the spectral step also skips the rows k_scan_outer cleared)
-    timed_alg = sum(alg.values()) - SPEC_SKIP_B + (PHYS_LAZY_B / args.steps)
+    timed_alg = sum(alg.values()) + (PHYS_LAZY_B / args.steps)
     roofline = {
         "bound": "hbm", "kernel": idle["kernel"], "achieved": idle["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": idle["frac"], "traffic": traffic.get(idle["kernel"]), "peak_kind": peak_kind,

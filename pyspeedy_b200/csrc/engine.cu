@@ -813,7 +813,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     CK(cudaEventRecord(E.ev0, E.stream));
     // multi-step call: look once at the coefficients outside the triangular truncation (k_scan_outer, dynamics.cu)
     E.outer_on = false;
-    if (nsteps >= 4 && !per_step_sync && g_scan_outer) {
+    if (((nsteps >= 4 && !per_step_sync) || (P.on && g_profile_intermediate)) && g_scan_outer) {
         CK(cudaMemsetAsync(E.d_outer, 1, (size_t)2 * nt * sizeof(int), E.stream));  // bytes 0x01: non-zero = "all zero so far"
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles)
             launch_scan_outer(E.stream, make_ctx(E.d_tiles + t0, E.d_masks + t0, std::min(E.chunk_tiles, nt - t0)), E.d_outer + 2 * t0);
