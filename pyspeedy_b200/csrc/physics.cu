@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     const int lane = threadIdx.x & 31, q = blockIdx.x * 4 + (threadIdx.x >> 5), t = blockIdx.y;
     const int j = q / IX;
     const size_t e = (size_t)q * TILE, lev = (size_t)NG * TILE;
-#define ST2D(v) (stp(c, t, c.off[v], lane) + e)
+#define ST2D(v) (stp_nc(c, t, c.off[v], lane) + e)
     // Register relief (three CTAs per SM instead of two): the long-wave transmissivities and the short-wave heating
     // (state, read-only on 2 of 3 steps) are copied straight into shared memory with cp.async while the first half of
     // the kernel runs, and the accumulated T tendency waits there between the condensation and the final sum.
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     const double *fb = c.G->fband;
     const bool do_sw = *(c.st + ((long long)tile0 * c.st_elems + c.off_slots + SL_SW) * TILE + lane) != 0.0;
     if (!(do_sw && act)) {  // on short-wave steps the values are produced below
-        const double *pt2 = stp(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp(c, t, c.off[V_tt_rsw], lane) + e;
+        const double *pt2 = stp_nc(c, t, c.off[V_rad_tau2], lane) + e, *ptr = stp_nc(c, t, c.off[V_tt_rsw], lane) + e;
 #pragma unroll
         for (int k = 0; k < 4 * KX; k++) cp_async8(sm + k * 128, pt2 + k * lev);
 #pragma unroll
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     {
         const bool sw = do_sw;
         if (!sw) {  // on short-wave steps these are produced below, not read
-            const double *pst = stp(c, t, c.off[V_rad_strat_corr], lane) + e;
+            const double *pst = stp_nc(c, t, c.off[V_rad_strat_corr], lane) + e;
             prefetch_l2(pst), prefetch_l2(pst + lev), prefetch_l2(ST2D(V_ssrd));
         } else {
             prefetch_l2(ST2D(V_zenit_correction)), prefetch_l2(ST2D(V_flux_solar_in)), prefetch_l2(ST2D(V_flux_ozone_upper));
@@ -312,9 +312,9 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
     }
 
     // ---- radiation
-    double *tau2 = stp(c, t, c.off[V_rad_tau2], lane) + e;  // (ix,il,kx,4): element (k, b) at (k + KX*b)*lev
-    double *ttrsw = stp(c, t, c.off[V_tt_rsw], lane) + e;
-    double *strat = stp(c, t, c.off[V_rad_strat_corr], lane) + e;
+    double *tau2 = stp_nc(c, t, c.off[V_rad_tau2], lane) + e;  // (ix,il,kx,4): element (k, b) at (k + KX*b)*lev
+    double *ttrsw = stp_nc(c, t, c.off[V_tt_rsw], lane) + e;
+    double *strat = stp_nc(c, t, c.off[V_rad_strat_corr], lane) + e;
     int icltop_out = 0;
     if (do_sw && act) {  // physics.f90:151-169 ; inactive lanes own no state
         // clouds (shortwave_radiation.f90:325-404)
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(128, PHYS_MINBLOCKS) k_physics(const Ctx c, co
         *ST2D(V_ssr) = ssr;
         // the reference leaves the SW-phase rad_flux(:,:,1:2) in state until the LW sweep overwrites them
         // long-wave transmissivities (section 5)
-        const double co2 = slot(c, t, lane, SL_CO2);
+        const double co2 = *stp_nc(c, t, c.off_slots + SL_CO2, lane);
         const double acl2 = cloudc * ABLCL2;
 #pragma unroll
         for (int k = 0; k < KX; k++) {

@@ -110,6 +110,13 @@ struct Ctx {
 __device__ __forceinline__ double *stp(const Ctx &c, int t, long long off, int lane) {
     return c.st + ((long long)c.tiles[t] * c.st_elems + off) * TILE + lane;
 }
+// The tile list is never written while a kernel runs: a non-coherent (invariant) load lets the compiler keep the tile index
+// in a register across stores instead of re-reading it for every state address (42 reloads in k_physics before this: 0.543
+// -> 0.516 ms per intermediate step at 512 members).  The short bandwidth-bound kernels keep stp: there the hoisted loads
+// cost registers (k_couple 48 -> 64, k_spec_step_vq 32 -> 42) and 3-5 % of their time.
+__device__ __forceinline__ double *stp_nc(const Ctx &c, int t, long long off, int lane) {
+    return c.st + ((long long)__ldg(c.tiles + t) * c.st_elems + off) * TILE + lane;
+}
 __device__ __forceinline__ double *scp(const Ctx &c, int t, long long off, int lane) {
     return c.scr + ((long long)t * c.scr_elems + off) * TILE + lane;
 }
