@@ -302,6 +302,17 @@ def run_config3(args):
     t_e2e = comm.max(time.perf_counter() - t0)
     comm.barrier()
     e2e_value = m_total * args.steps / NSTEPS_DAY / t_e2e
+    # ---- the reference's strict loop for comparison: one parallel_step driver call per step, every output of every step
+    #      stored (no multi-step call anywhere), host handle arrays in and error codes out per step
+    k_strict = min(args.steps, 12)
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_strict):
+        assert (_speedy.parallel_step(s, c) == 0).all()
+    lib.spdy_synchronize()
+    t_strict = comm.max(time.perf_counter() - t0)
+    comm.barrier()
+    strict_value = m_total * k_strict / NSTEPS_DAY / t_strict
     stats_bytes = 2 * (5 * 96 * 48 * 8 + 96 * 48) * 8
     n_calls = -(-args.steps // NSTEPS_DAY)  # driver calls of the run loop: one per callback interval
     # per driver call: state / control handle arrays in, error codes out; per output time: date containers + date in,
@@ -363,11 +374,19 @@ def run_config3(args):
                    if m_total == 4096 else f"T30L8 {m_total}-member perturbed-IC ensemble",
                    "members": m_total, "members_per_gpu": m_local, "grid": "96x48x8, T30", "steps_per_day": 36,
                    "l2": "state (11.7 MiB/member) + scratch far exceed the 126 MB L2: no flush needed",
-                   "collective": "ncclAllReduce(sum, f64) of 377,856 doubles per output time, issued by libspeedy_b200.so"},
+                   "collective": "ncclAllReduce(sum, f64) of 377,856 doubles per output time, issued by libspeedy_b200.so",
+                   "multi_step_call": "value = ONE spdy_run_steps call of K steps: intermediate steps do not store the 39 "
+                                      "doubles per column of physics outputs that nothing reads before the next step "
+                                      "overwrites them and skip spectral rows the time filter cannot change; the state "
+                                      "after the call is bit-identical to K per-step calls (tests/test_ensemble_gpu.py); "
+                                      "e2e.per_step_calls is the loop that stores everything on every step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * t_e2e / args.steps, "daily_output_ms": 1e3 * out.seconds / max(out.calls, 1),
                 "daily_outputs": out.calls,
-                "path": "SpeedyEns.run(callbacks=[DiagnosticCheck(36), EnsembleStatistics(36)])"},
+                "path": "SpeedyEns.run(callbacks=[DiagnosticCheck(36), EnsembleStatistics(36)]): one multi-step driver "
+                        "call per callback interval",
+                "per_step_calls": {"value": strict_value, "unit": UNIT, "steps": k_strict,
+                                   "path": "parallel_step once per step: every step stores every output"}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
