@@ -143,3 +143,81 @@ def test_hdf5_reader_on_the_reference_boundary_file():
     # the NetCDF-3 fixtures of the reference are not HDF5: a clear error, not garbage
     with pytest.raises(ValueError):
         hdf5_reader.load("/root/reference/pyspeedy/tests/fixtures/1982-01-02_0000.nc")
+
+
+def test_run_loop_batching_logic(monkeypatch):
+    """SpeedyEns.run without a GPU: which driver calls the loop makes for which callbacks (pyspeedy/speedy.py:547-593 calls
+    every callback after every step; the stock ones act when step % interval == 0, pyspeedy/callbacks.py:48-58)."""
+    from datetime import timedelta
+
+    from pyspeedy_b200 import speedy as sp
+    from pyspeedy_b200.callbacks import BaseCallback
+
+    calls, fired = [], []
+
+    class FakeDriver:
+        @staticmethod
+        def run_steps(s, c, n):
+            calls.append(n)
+            return np.zeros(len(s), dtype=np.int32)
+
+        @staticmethod
+        def parallel_step(s, c):
+            calls.append(1)
+            return np.zeros(len(s), dtype=np.int32)
+
+        @staticmethod
+        def set_datetimes(d, when):
+            pass
+
+    class Member:
+        _model_date = 1
+        end_date = datetime(1982, 1, 3)
+
+    def make(step0=0):
+        e = sp.SpeedyEns.__new__(sp.SpeedyEns)
+        e.comm, e.n_total, e.n_members, e.members = None, 2, 2, [Member(), Member()]
+        e.current_date = datetime(1982, 1, 3) - timedelta(days=2)
+        e._step = step0
+        e.handles = lambda: (np.array([1, 2], dtype=np.int64), np.array([1, 2], dtype=np.int64))
+        e.get_current_step = lambda: e._step + sum(calls)
+        return e
+
+    class Every(BaseCallback):
+        def __init__(self, interval):
+            super().__init__(interval=interval)
+
+        def __call__(self, model):
+            if not self.skip_flag(model):
+                fired.append((self.interval, model.get_current_step()))
+
+    monkeypatch.setattr(sp, "_speedy", FakeDriver)
+    # two stock callbacks: stop exactly where one of them acts, never more than a simulated day per call
+    make().run(callbacks=[Every(24), Every(36)])
+    assert calls == [24, 12, 12, 24] and fired == [(24, 24), (36, 36), (24, 48), (24, 72), (36, 72)]
+    # a start that is not a multiple of the intervals
+    calls.clear(), fired.clear()
+    make(step0=30).run(callbacks=[Every(36)])
+    assert calls == [6, 36, 30] and [s for _, s in fired] == [36, 72]
+    # no callbacks: a day per call; an explicit steps_per_call is honoured; 1 = the reference's loop
+    calls.clear()
+    make().run()
+    assert calls == [36, 36]
+    calls.clear()
+    make().run(callbacks=[Every(36)], steps_per_call=10)
+    assert calls == [10] * 7 + [2]
+    calls.clear()
+    make().run(callbacks=[Every(36)], steps_per_call=1)
+    assert calls == [1] * 72
+    # a plain callable, or a subclass with its own skip_flag, may act at any step: one driver call per step
+    calls.clear()
+    make().run(callbacks=[lambda m: None])
+    assert calls == [1] * 72
+
+    class Own(Every):
+        def skip_flag(self, model):
+            return model.get_current_step() % 7 != 0
+
+    calls.clear(), fired.clear()
+    make().run(callbacks=[Own(36)])
+    assert calls == [1] * 72 and [s for _, s in fired] == list(range(7, 73, 7))
