@@ -759,6 +759,15 @@ static inline double now_us() {
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 static bool g_profile_intermediate = getenv("SPDY_PROFILE_INTERMEDIATE") && atoi(getenv("SPDY_PROFILE_INTERMEDIATE")) != 0;
+// per-tile buffers of a driver call: error codes (device + pinned host) and the Ctx::outer_zero flags, grown together
+static void ensure_err_capacity(int nt) {
+    if (nt * TILE <= E.err_cap) return;
+    if (E.d_err) CK(cudaFree(E.d_err)), CK(cudaFreeHost(E.h_err)), CK(cudaFree(E.d_outer));
+    E.err_cap = nt * TILE;
+    CK(cudaMalloc(&E.d_err, E.err_cap * sizeof(int)));
+    CK(cudaMalloc(&E.d_outer, 2 * nt * sizeof(int)));
+    CK(cudaMallocHost(&E.h_err, E.err_cap * sizeof(int)));
+}
 static const bool g_scan_outer = !(getenv("SPDY_SCAN_OUTER") && atoi(getenv("SPDY_SCAN_OUTER")) == 0);
 static const bool g_lazy_diag = !(getenv("SPDY_LAZY_DIAG") && atoi(getenv("SPDY_LAZY_DIAG")) == 0);
 static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps, int *err_out, bool per_step_sync) {
@@ -787,13 +796,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     }
     if (run.empty()) return failed;
     const int nt = prepare_members(run.data(), (int)run.size());
-    if (nt * TILE > E.err_cap) {
-        if (E.d_err) CK(cudaFree(E.d_err)), CK(cudaFreeHost(E.h_err)), CK(cudaFree(E.d_outer));
-        E.err_cap = nt * TILE;
-        CK(cudaMalloc(&E.d_err, E.err_cap * sizeof(int)));
-        CK(cudaMalloc(&E.d_outer, 2 * nt * sizeof(int)));
-        CK(cudaMallocHost(&E.h_err, E.err_cap * sizeof(int)));
-    }
+    ensure_err_capacity(nt);
     std::map<int, int> tile_pos;
     for (int t = 0; t < nt; t++) tile_pos[E.cached_tiles[t]] = t;
     std::vector<int> epos(run.size());  // position of each member's error code in the read-back buffer

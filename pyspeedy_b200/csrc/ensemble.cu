@@ -361,12 +361,7 @@ int spdy_batch_check(const int64_t *states, int n, int *error_codes) {
     for (int i = 0; i < n; i++) error_codes[i] = member_of(states[i]) ? 0 : -1;
     const int nt = prepare_members(states, n);
     if (nt == 0) return 0;
-    if (nt * TILE > E.err_cap) {
-        if (E.d_err) CK(cudaFree(E.d_err)), CK(cudaFreeHost(E.h_err));
-        E.err_cap = nt * TILE;
-        CK(cudaMalloc(&E.d_err, E.err_cap * sizeof(int)));
-        CK(cudaMallocHost(&E.h_err, E.err_cap * sizeof(int)));
-    }
+    ensure_err_capacity(nt);
     for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
         const int ntc = std::min(E.chunk_tiles, nt - t0);
         Ctx c = make_ctx(E.d_tiles + t0, E.d_masks + t0, ntc);

@@ -244,3 +244,28 @@ def test_sticky_error_in_multistep_call(oracle):
     # per-step driver call: same code, date of the failed member not advanced on the host mirror either
     e1 = _speedy.parallel_step(s, c)
     assert e1[2] == -2 and e1[0] == 0
+
+
+def test_check_before_the_first_multistep_call():
+    """Regression (round 2): the batched check and the step driver grow the same per-tile buffers; a check made BEFORE
+    the first multi-step call left the outer-coefficient flags unallocated.  Fresh process, so the order is what it says."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "from datetime import datetime\n"
+        "import numpy as np\n"
+        "from pyspeedy_b200 import SpeedyEns, _speedy\n"
+        "e = SpeedyEns(70, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 2))\n"
+        "e.set_bc()\n"
+        "e.check()\n"
+        "s, c = e.handles()\n"
+        "assert (_speedy.run_steps(s, c, 6) == 0).all()\n"
+        "assert (_speedy.run_steps(s[:3], c[:3], 5) == 0).all()\n"
+        "e.check()\n"
+        "assert e.members[69]['current_step'] == 6 and e.members[1]['current_step'] == 11\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
