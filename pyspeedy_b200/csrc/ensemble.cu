@@ -149,8 +149,38 @@ struct EnsBuffers {
     size_t stage_cap = 0;
     int2 *d_who = nullptr;
     int who_cap = 0;
+    char *h_pin[2] = {nullptr, nullptr};  // pinned bounce buffers of the bulk getter
+    cudaEvent_t ev_pin[2];
 };
 static EnsBuffers EB;
+constexpr size_t ENS_PIN_CHUNK = (size_t)8 << 20;
+
+// device -> pageable host memory through two pinned bounce buffers: the copy into pinned memory runs at PCIe speed and
+// overlaps the host memcpy of the previous chunk (a direct cudaMemcpy into a numpy array runs at a third of that)
+static void d2h_bounced(void *dst, const void *src, size_t bytes) {
+    if (!EB.h_pin[0]) {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMallocHost(&EB.h_pin[i], ENS_PIN_CHUNK));
+            CK(cudaEventCreateWithFlags(&EB.ev_pin[i], cudaEventDisableTiming));
+        }
+    }
+    size_t prev_off = 0, prev_n = 0;
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += ENS_PIN_CHUNK, k++) {
+        const size_t nb = std::min(ENS_PIN_CHUNK, bytes - off);
+        CK(cudaMemcpyAsync(EB.h_pin[k & 1], (const char *)src + off, nb, cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaEventRecord(EB.ev_pin[k & 1], E.stream));
+        if (prev_n) {
+            CK(cudaEventSynchronize(EB.ev_pin[(k - 1) & 1]));
+            memcpy((char *)dst + prev_off, EB.h_pin[(k - 1) & 1], prev_n);
+        }
+        prev_off = off, prev_n = nb;
+    }
+    if (prev_n) {
+        CK(cudaEventSynchronize(EB.ev_pin[(k - 1) & 1]));
+        memcpy((char *)dst + prev_off, EB.h_pin[(k - 1) & 1], prev_n);
+    }
+}
 
 }  // namespace spdy
 
@@ -348,8 +378,7 @@ int spdy_ensemble_get(const int64_t *states, int n, int var, void *dst, size_t b
         else
             k_gather_members<double><<<grid, 256, 0, E.stream>>>(E.st, E.st_elems, E.off[var], ne, EB.d_who, i0 + nb, i0, (double *)EB.d_stage);
         COUNT(1);
-        CK(cudaMemcpyAsync((char *)dst + (size_t)i0 * per, EB.d_stage, (size_t)nb * per, cudaMemcpyDeviceToHost, E.stream));
-        CK(cudaStreamSynchronize(E.stream));
+        d2h_bounced((char *)dst + (size_t)i0 * per, EB.d_stage, (size_t)nb * per);
     }
     return 0;
 }
