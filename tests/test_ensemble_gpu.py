@@ -269,3 +269,24 @@ def test_check_before_the_first_multistep_call():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_multistep_calls_across_day_boundaries():
+    """80 steps as two multi-step calls (37 + 43: both cross a daily forcing / coupler boundary and end off the short-wave
+    phase) against 80 per-step calls, on perturbed members of one tile: every registry variable bit-identical."""
+    from pyspeedy_b200 import MODEL_STATE_DEF, SpeedyEns, _speedy
+
+    e = SpeedyEns(6, start_date=datetime(1982, 1, 1), end_date=datetime(1982, 1, 4))
+    e.set_bc(perturb_sigma=0.05, seed=11)
+    s, c = e.handles()
+    _speedy.clone_state(int(s[0]), s[3:4]), _speedy.clone_state(int(s[1]), s[4:5]), _speedy.clone_state(int(s[2]), s[5:6])
+    assert (_speedy.run_steps(s[:3], c[:3], 37) == 0).all()
+    assert (_speedy.run_steps(s[:3], c[:3], 43) == 0).all()
+    for _ in range(80):
+        assert (_speedy.parallel_step(s[3:], c[3:]) == 0).all()
+    for k in range(3):
+        assert _speedy.get_model_datetime(int(s[k])) == _speedy.get_model_datetime(int(s[k + 3]))
+        for v in MODEL_STATE_DEF:
+            x, y = np.asarray(e.members[k][v]), np.asarray(e.members[k + 3][v])
+            assert np.array_equal(x, y, equal_nan=True), (k, v)
+    assert not np.array_equal(np.asarray(e.members[0]["t"]), np.asarray(e.members[1]["t"]))
