@@ -49,7 +49,11 @@ int spdy_shape(int64_t state, int var, int *dims /* [5] */, int *ndim);
 
 /* ---- ensemble extensions (no reference counterpart; same semantics as repeated parallel_step) ------------- */
 /* Advance all listed members `nsteps` steps without a host round trip per step; error_codes receives the first
- * non-zero code of each member (0 if none).  Returns the number of failed members. */
+ * non-zero code of each member (0 if none; a failing member is frozen at its failing step).  Returns the number of
+ * failed members.  When the call returns, every registry variable holds what `nsteps` spdy_parallel_step calls leave,
+ * bit for bit; in between -- where nothing can observe the state -- the column physics does not store the outputs that no
+ * kernel reads and the next step overwrites, and the spectral steps skip coefficients outside the triangular truncation
+ * on which the time filter is the identity (SPDY_LAZY_DIAG=0 / SPDY_SCAN_OUTER=0 switch both off). */
 int spdy_run_steps(const int64_t *states, const int64_t *controls, int n_members, int nsteps, int *error_codes);
 int spdy_reserve(int n_members);            /* pre-size the device arenas */
 /* SPPT, stochastically perturbed parametrisation tendencies (sppt.f90:40-146, physics.f90:233-248; the reference's
