@@ -424,7 +424,7 @@ def run_config1(args):
     line = base_line(1.0 / dt, UNIT, NSTEPS_DAY, NSTEPS_DAY, 1e3 * dt / NSTEPS_DAY,
                      "T30L8 single-member 1-day forecast (BASELINE configs[0])", members=1)
     line["e2e"] = {"value": 1.0 / dt2, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4 + 41 * 4608 * 8 // NSTEPS_DAY,
-                   "path": "Speedy.run(callbacks=[ModelCheckpoint(36)]): one step() driver call per step"}
+                   "path": "Speedy.run(callbacks=[ModelCheckpoint(36)]): one multi-step driver call per callback interval"}
     line["gpu_launches"] = int(launches)
     print(json.dumps(line))
 

@@ -270,19 +270,42 @@ class Speedy:
         self["sst_anom"] = np.asarray(ssta, dtype=np.float64)
         self._initialized_ssta = True
 
-    def run(self, callbacks=None):
-        """Run the model between the start and end dates (pyspeedy/speedy.py:375-405)."""
+    def run(self, callbacks=None, steps_per_call=None):
+        """Run the model between the start and end dates (pyspeedy/speedy.py:375-405).
+
+        As in :meth:`SpeedyEns.run`: when every callback is a stock ``BaseCallback`` (acts when ``step % interval == 0``)
+        the model is advanced by one multi-step driver call up to the next step at which one of them acts;
+        ``steps_per_call=1`` is the reference's loop, one ``step`` driver call per model step."""
         if callbacks is None:
             callbacks = list()
         if not self._initialized_bc:
             raise RuntimeError("The SPEEDY model was not initialized. Call the `set_bc` method to initialize the model.")
         self.current_date = self.start_date
         dt_step = timedelta(seconds=3600 * 24 / 36)
-        while self.current_date < self.end_date:
-            error_code = _speedy.step(self._state_cnt, self._control_cnt)
+        intervals = None
+        if steps_per_call is None:
+            from pyspeedy_b200.callbacks import BaseCallback
+
+            if all(isinstance(cb, BaseCallback) and type(cb).skip_flag is BaseCallback.skip_flag for cb in callbacks):
+                intervals = [max(1, int(cb.interval)) for cb in callbacks]
+            else:
+                steps_per_call = 1
+        step = self.get_current_step() if intervals else 0
+        end_date, date = self.end_date, self.current_date
+        s, c = np.array([self._state_cnt], dtype=np.int64), np.array([self._control_cnt], dtype=np.int64)
+        while date < end_date:
+            left = int(round((end_date - date) / dt_step))
+            n = min([36] + [i - step % i for i in intervals]) if intervals is not None else steps_per_call
+            n = max(1, min(n, left))
+            if n > 1:
+                error_code = int(_speedy.run_steps(s, c, n)[0])
+            else:
+                error_code = _speedy.step(self._state_cnt, self._control_cnt)
             if error_code < 0:
                 raise RuntimeError(ERROR_CODES[error_code])
-            self.current_date += dt_step
+            step += n
+            date += n * dt_step
+            self.current_date = date
             for callback in callbacks:
                 callback(self)
 
