@@ -130,7 +130,7 @@ struct Engine {
     InvDesc *d_inv[2] = {nullptr, nullptr};  // j2 = 1, 2 (77 fields; 85 with the SPPT pattern levels appended)
     bool sppt_on = false;
     int diag_out = 1;  // Ctx::diag_out of the step being launched (step_members)
-    int *d_outer = nullptr;  // Ctx::outer_zero flags of the tiles of the current multi-step call (size err_cap / TILE)
+    int *d_outer = nullptr;  // Ctx::outer_zero flags of the current multi-step call: two per tile (ensure_err_capacity)
     bool outer_on = false;
     unsigned long long sppt_seed = 0;
     FwdDesc *d_fwd[FM_NMODES] = {};
@@ -817,7 +817,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
     // multi-step call: look once at the coefficients outside the triangular truncation (k_scan_outer, dynamics.cu)
     E.outer_on = false;
     if (((nsteps >= 4 && !per_step_sync) || (P.on && g_profile_intermediate)) && g_scan_outer) {
-        CK(cudaMemsetAsync(E.d_outer, 1, (size_t)2 * nt * sizeof(int), E.stream));  // bytes 0x01: non-zero = "all zero so far"
+        CK(cudaMemsetAsync(E.d_outer, 1, (size_t)2 * nt * sizeof(int), E.stream));  // bytes 0x01: non-zero = "nothing found that moves"
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles)
             launch_scan_outer(E.stream, make_ctx(E.d_tiles + t0, E.d_masks + t0, std::min(E.chunk_tiles, nt - t0)), E.d_outer + 2 * t0);
         COUNT((nt + E.chunk_tiles - 1) / E.chunk_tiles);
@@ -831,7 +831,7 @@ static int step_members(const int64_t *hs, const int64_t *cs, int n, int nsteps,
         bool early = false;
         // outputs of the column physics that no kernel reads (fluxes, precipitation, rad_flux, rad_st4a: 39 of the ~160
         // doubles a column moves per step) are stored by the LAST step of a multi-step call only: nothing can observe the
-        // values the intermediate steps would have left there (tests/test_model_gpu.py::test_run_steps_equals_single_steps)
+        // values the intermediate steps would have left there (tests/test_ensemble_gpu.py::test_multistep_call_leaves_the_complete_state)
         E.diag_out = (per_step_sync || s == nsteps - 1 || !g_lazy_diag) ? 1 : 0;
         if (P.on && g_profile_intermediate) E.diag_out = 0;  // spdy_profile_step timing an intermediate step (bench.py)
         for (int t0 = 0; t0 < nt; t0 += E.chunk_tiles) {
