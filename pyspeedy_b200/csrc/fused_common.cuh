@@ -26,27 +26,6 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-// Two FFT lines per thread (the same latitude, two neighbouring members): the generated butterfly items (fft96_gen.cuh) are
-// templates on the value type, and with D2 every shared-memory access of an FFT warp is 128 bits wide -- half the LDS /
-// STS instructions per line and two independent dependency chains per thread.
-struct __align__(16) D2 {
-    double x, y;
-};
-__device__ __forceinline__ D2 operator+(const D2 a, const D2 b) { return D2{a.x + b.x, a.y + b.y}; }
-__device__ __forceinline__ D2 operator-(const D2 a, const D2 b) { return D2{a.x - b.x, a.y - b.y}; }
-__device__ __forceinline__ D2 operator-(const D2 a) { return D2{-a.x, -a.y}; }
-__device__ __forceinline__ D2 operator*(const double s, const D2 a) { return D2{s * a.x, s * a.y}; }
-__device__ __forceinline__ D2 operator*(const D2 a, const double s) { return D2{a.x * s, a.y * s}; }
-struct LdSlot2 {  // stage-A loader for a pair of members: Fourier row r of a slot
-    const double *p;
-    __device__ __forceinline__ D2 operator()(int r) const { return *reinterpret_cast<const D2 *>(p + r * MQ_NM); }
-};
-struct StExch2 {  // in-place stage-B store for a pair of lines (see StExchK), optional 1/cos(lat) factor
-    D2 *p;
-    double sc;
-    bool scale;
-    __device__ __forceinline__ void operator()(int i, D2 v) const { p[(i >> 3) * 32] = scale ? v * sc : v; }
-};
 struct LdSlot {  // FFT stage-A loader: Fourier row r of a slot, this thread's member
     const double *p;
     __device__ __forceinline__ double operator()(int r) const { return p[r * MQ_NM]; }
@@ -66,7 +45,7 @@ struct StExchK {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// nlat = latitude rows per box: 4 (quad per hemisphere) or 8 (octet per hemisphere)
+// nlat = latitude rows per box: 4 (quad per hemisphere); 8 (octet per hemisphere) is used by tools/experiments/fused_mma5.cu only
 static const CUtensorMap &s2g2_tensor_map(const Ctx &c, const int nlat = 4) {
     static EncodeTiledFn encode = nullptr;
     static CUtensorMap maps[2];

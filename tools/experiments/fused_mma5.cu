@@ -19,6 +19,29 @@
 
 namespace spdy {
 
+// Two FFT lines per thread (the same latitude, two neighbouring members): the generated butterfly items (fft96_gen.cuh) are
+// templates on the value type, and with D2 every shared-memory access of an FFT warp is 128 bits wide -- half the LDS /
+// STS instructions per line and two independent dependency chains per thread.
+struct __align__(16) D2 {
+    double x, y;
+};
+__device__ __forceinline__ D2 operator+(const D2 a, const D2 b) { return D2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ D2 operator-(const D2 a, const D2 b) { return D2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ D2 operator-(const D2 a) { return D2{-a.x, -a.y}; }
+__device__ __forceinline__ D2 operator*(const double s, const D2 a) { return D2{s * a.x, s * a.y}; }
+__device__ __forceinline__ D2 operator*(const D2 a, const double s) { return D2{a.x * s, a.y * s}; }
+struct LdSlot2 {  // stage-A loader for a pair of members: Fourier row r of a slot
+    const double *p;
+    __device__ __forceinline__ D2 operator()(int r) const { return *reinterpret_cast<const D2 *>(p + r * MQ_NM); }
+};
+struct StExch2 {  // in-place stage-B store for a pair of lines (see StExchK), optional 1/cos(lat) factor
+    D2 *p;
+    double sc;
+    bool scale;
+    __device__ __forceinline__ void operator()(int i, D2 v) const { p[(i >> 3) * 32] = scale ? v * sc : v; }
+};
+
+
 constexpr int P5_XH = IX * 64;  // doubles per exchange buffer (64 lines)
 constexpr size_t P5_SMEM = ((size_t)2 * P3_SLOT + 2 * P5_XH) * sizeof(double);
 static_assert(P5_SMEM <= 232448, "shared memory per CTA on sm_100a");
